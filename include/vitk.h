@@ -1,0 +1,155 @@
+/* vitk — C ABI of the B200 (sm_100a) kernel library behind the ViT-B/16 fine-tuning hot path.
+ *
+ * This is the drop-in boundary.  The reference (/root/reference/ViT-Training.py:83-90,120-132)
+ * reaches the hot path through PyTorch modules of HuggingFace transformers
+ * (HF = transformers/models/vit/modeling_vit.py, v5.5.0), which dispatch to ATen operators.
+ * Each entry point below replaces the ATen operator(s) named in its comment; the Python side
+ * (chest-x-ray-vit_b200/ops.py) binds them with ctypes and exposes them as torch custom ops.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes only.  All pointers are DEVICE pointers unless
+ *     named host_*.  bf16 buffers are passed as void* / uint16_t*.
+ *   - every call is asynchronous on `stream` (a cudaStream_t); nothing synchronises the host,
+ *     nothing allocates or frees device memory.  Workspaces are caller-provided.
+ *   - return 0 on success, >0 = cudaError_t, <0 = argument/shape error (VITK_E*).
+ *     vitk_last_error() returns a thread-local message for the last non-zero return.
+ *   - thread-safe / re-entrant (PyTorch calls backward from its autograd thread).
+ */
+#ifndef VITK_H_
+#define VITK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define VITK_API __attribute__((visibility("default")))
+#else
+#define VITK_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VITK_VERSION 100
+
+#define VITK_EINVAL (-1)   /* bad argument / unsupported shape */
+#define VITK_EALIGN (-2)   /* pointer or leading dimension not aligned as required */
+#define VITK_EDEVICE (-3)  /* not an sm_100 device */
+#define VITK_EDRIVER (-4)  /* cuTensorMapEncodeTiled unavailable / failed */
+
+typedef void* vitk_stream_t; /* cudaStream_t */
+
+VITK_API int vitk_version(void);
+/* 0 iff device `dev` has compute capability 10.x; the library refuses to run elsewhere. */
+VITK_API int vitk_check_device(int dev);
+VITK_API const char* vitk_last_error(void);
+
+/* ------------------------------------------------------------------ input normalisation
+ * Replaces ToTensor+Normalize on img.convert("RGB") (ViT-Training.py:60-66) fused with the
+ * im2col of Conv2d(k=s=patch) (HF:151,166).  gray u8 [B,H,W] → bf16 [B*(H/p)*(W/p), 3*p*p],
+ * column k = c*p*p + ky*p + kx, value (g/255 - mean[c]) / std[c].  host_mean/std: 3 floats. */
+VITK_API int vitk_patchify_u8(const uint8_t* gray, int64_t B, int64_t H, int64_t W, int64_t patch,
+                     const float* host_mean, const float* host_std, void* out_bf16, vitk_stream_t stream);
+/* Same im2col for the drop-in fp32 NCHW input [B,3,H,W] (collate_fn, ViT-Training.py:77-80). */
+VITK_API int vitk_patchify_f32(const float* pixel_values, int64_t B, int64_t H, int64_t W, int64_t patch,
+                      void* out_bf16, vitk_stream_t stream);
+
+/* ------------------------------------------------------------------ LayerNorm
+ * Replaces aten::native_layer_norm / native_layer_norm_backward (HF:325-326,333,340,455).
+ * x fp32 [M,D] (row stride ldx elements) → y bf16 [M,D]; mean/rstd fp32 [M] saved for backward. */
+VITK_API int vitk_layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps,
+                       int64_t M, int64_t D, void* y_bf16, float* mean, float* rstd, vitk_stream_t stream);
+/* dx = dres + LNbwd(dy) (bf16 [M,D]; dres may be NULL); dgamma/dbeta fp32 [D] are ACCUMULATED
+ * (+=) with atomics, so zero them first for a plain gradient. */
+VITK_API int vitk_layernorm_bwd(const void* dy_bf16, const float* x, int64_t ldx, const float* mean, const float* rstd,
+                       const float* gamma, const void* dres_bf16, int64_t M, int64_t D, void* dx_bf16,
+                       float* dgamma, float* dbeta, vitk_stream_t stream);
+
+/* ------------------------------------------------------------------ dense contraction
+ * Replaces aten::addmm / aten::mm (+ fused bias/GELU/residual elementwise ops) for the patch
+ * embedding, QKV, attention-output and MLP projections and their dgrad/wgrad (HF:166,228-230,
+ * 266,297-298,309-311).  D[M,N] = A·Bᵀ with logical A [M,K], logical B [N,K], bf16 in, fp32
+ * accumulate in TMEM (tcgen05.mma), operands staged by TMA.
+ *   a_mn_major = 0: A stored [M,K] with K contiguous, lda = row stride (elements)
+ *   a_mn_major = 1: A stored [K,M] with M contiguous, lda = stride between k-rows
+ *   (same for B with N).  lda/ldb multiples of 8, base pointers 16-byte aligned.
+ * N must be a multiple of 128. */
+enum vitk_epilogue {
+  VITK_EPI_STORE_BF16 = 0,      /* d bf16 = acc                                  (dgrad)   */
+  VITK_EPI_BIAS_BF16 = 1,       /* d bf16 = acc + bias[n]                        (QKV)     */
+  VITK_EPI_BIAS_GELU_BF16 = 2,  /* d bf16 = u = acc + bias; d2 bf16 = gelu_erf(u) (fc1)    */
+  VITK_EPI_BIAS_RESID_F32 = 3,  /* d f32 = acc + bias[n] + aux_f32[m,n]          (out, fc2)*/
+  VITK_EPI_PATCH_F32 = 4,       /* d f32[(m/rows_in)*rows_out + row_off + m%rows_in, n] =
+                                   acc + bias[n] + aux_f32[row_off + m%rows_in, n] (patch+pos) */
+  VITK_EPI_DGELU_BF16 = 5,      /* d bf16 = acc * gelu'(aux_bf16[m,n])           (fc2 dgrad)*/
+  VITK_EPI_ACCUM_F32 = 6,       /* d f32 += acc (red.global.add; split-K allowed) (wgrad)  */
+  VITK_EPI_STORE_F32 = 7        /* d f32 = acc                                             */
+};
+
+typedef struct vitk_gemm_args {
+  const void* a;
+  const void* b;
+  int64_t M, N, K;
+  int64_t lda, ldb;
+  int32_t a_mn_major, b_mn_major;
+  int32_t epilogue;      /* enum vitk_epilogue */
+  int32_t split_k;       /* >=1; >1 only with VITK_EPI_ACCUM_F32; 0 = library chooses */
+  void* d;
+  int64_t ldd;
+  void* d2;              /* second output (same ldd), VITK_EPI_BIAS_GELU_BF16 only */
+  const float* bias;     /* [N] or NULL */
+  const void* aux;       /* residual f32 / pos f32 / pre-activation bf16, row stride ld_aux */
+  int64_t ld_aux;
+  int64_t rows_in, rows_out, row_off; /* VITK_EPI_PATCH_F32 row remap */
+  int32_t tile_n;        /* 0 = library chooses; else 128, 192 or 256 */
+  int32_t max_ctas;      /* 0 = all SMs; else cap on the persistent grid */
+} vitk_gemm_args;
+
+VITK_API int vitk_gemm_bf16(const vitk_gemm_args* args, vitk_stream_t stream);
+
+/* Column sums (bias gradients, aten::sum over rows): out f32 [N] += Σ_m x_bf16[m,n]. */
+VITK_API int vitk_colsum_bf16(const void* x_bf16, int64_t M, int64_t N, int64_t ldx, float* out, vitk_stream_t stream);
+
+/* ------------------------------------------------------------------ attention
+ * Replaces aten::scaled_dot_product_attention fwd/bwd (HF:232-246, sdpa_attention.py:92-102):
+ * softmax(Q·Kᵀ·scale)·V per (batch, head), no mask, no dropout, head_dim 64.
+ * qkv bf16 [B,T,3,H,64] (the fused QKV projection output, row stride 3*H*64);
+ * o bf16 [B,T,H*64]; lse fp32 [B,H,T] (natural-log sum-exp of the scaled scores). */
+VITK_API int vitk_attn_fwd(const void* qkv_bf16, int64_t B, int64_t T, int64_t H, float scale, void* o_bf16, float* lse,
+                  vitk_stream_t stream);
+/* dqkv bf16 [B,T,3,H,64].  workspace: vitk_attn_bwd_workspace_bytes(B,T,H) bytes. */
+VITK_API size_t vitk_attn_bwd_workspace_bytes(int64_t B, int64_t T, int64_t H);
+VITK_API int vitk_attn_bwd(const void* qkv_bf16, const void* o_bf16, const void* do_bf16, const float* lse, int64_t B,
+                  int64_t T, int64_t H, float scale, void* dqkv_bf16, void* workspace, vitk_stream_t stream);
+
+/* ------------------------------------------------------------------ embeddings glue
+ * CLS rows of the embedding output (HF:117-124): h[b,0,:] = cls + pos[0]. */
+VITK_API int vitk_embed_cls(const float* cls, const float* pos, int64_t B, int64_t T, int64_t D, float* h, vitk_stream_t stream);
+/* Backward of cat(cls,patches)+pos: dpos[t] += Σ_b dh[b,t]; dcls += Σ_b dh[b,0];
+ * dbias += Σ_{b,t>=1} dh[b,t]; dpatch bf16 [B*(T-1), D] = dh[b,1+p] (compact, for the wgrad GEMM). */
+VITK_API int vitk_embed_bwd(const void* dh_bf16, int64_t B, int64_t T, int64_t D, float* dpos, float* dcls, float* dbias,
+                   void* dpatch_bf16, vitk_stream_t stream);
+
+/* ------------------------------------------------------------------ head + loss
+ * Replaces final LayerNorm on the CLS rows, classifier Linear(D→C) and BCEWithLogitsLoss (mean)
+ * with their gradients (HF:455,641-646; loss_utils.py:110-112).
+ *   h f32 [B,T,D] (only rows t=0 are read); labels f32 [B,C] or NULL (then no loss/backward).
+ *   outputs: logits f32 [B,C]; loss f32 [1]; when labels != NULL and dh != NULL:
+ *   dh bf16 [B,T,D] rows t=0 = gradient, (all other rows are NOT touched — zero them once);
+ *   dWc [C,D], dbc [C], dgamma [D], dbeta [D] are ACCUMULATED.  loss_scale multiplies dlogits
+ *   (1.0 for a plain mean over B*C). */
+VITK_API int vitk_head_bce(const float* h, int64_t B, int64_t T, int64_t D, int64_t C, const float* gamma, const float* beta,
+                  float eps, const float* Wc, const float* bc, const float* labels, float loss_scale, float* logits,
+                  float* loss, void* dh_bf16, float* dWc, float* dbc, float* dgamma, float* dbeta,
+                  vitk_stream_t stream);
+
+/* ------------------------------------------------------------------ parameter shadow / misc
+ * bf16 shadow refresh after optimizer.step(): dst_bf16[i] = bf16(src[i]). n multiple of 8. */
+VITK_API int vitk_cast_f32_bf16(const float* src, void* dst_bf16, int64_t n, vitk_stream_t stream);
+VITK_API int vitk_fill_zero(void* ptr, size_t bytes, vitk_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VITK_H_ */
