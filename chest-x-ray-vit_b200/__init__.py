@@ -1,0 +1,26 @@
+"""B200-native (sm_100a) replacement for the ViT-B/16 fine-tuning hot path of
+Sam1rShaban1/Chest-X-Ray-ViT: the HuggingFace ViTForImageClassification forward/backward that
+ViT-Training.py:83-132 drives.  Public surface:
+
+  ViTConfig, ViTForImageClassification ... drop-in nn.Module (modeling.py)
+  ops ................................... tensor-level wrappers over the C ABI (include/vitk.h)
+  VitkAdamW ............................. flat-buffer AdamW + grad clip (optim.py)
+  GradSync .............................. bucketed NCCL gradient all-reduce (parallel.py)
+"""
+from . import _lib, ops  # noqa: F401
+
+__all__ = ["ops", "_lib"]
+
+
+def __getattr__(name):
+    # heavier modules are imported lazily so `import chest_x_ray_vit_b200` stays cheap
+    if name in ("ViTConfig", "ViTForImageClassification", "ImageClassifierOutput"):
+        from . import modeling
+        return getattr(modeling, name)
+    if name == "VitkAdamW":
+        from .optim import VitkAdamW
+        return VitkAdamW
+    if name == "GradSync":
+        from .parallel import GradSync
+        return GradSync
+    raise AttributeError(name)

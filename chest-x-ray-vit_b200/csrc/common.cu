@@ -2,6 +2,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace vitk {
@@ -21,6 +23,9 @@ int cuda_error(cudaError_t e, const char* what) {
   return static_cast<int>(e);
 }
 
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
 int num_sms() {
   static thread_local int cached_dev = -1;
   static thread_local int cached = 0;
@@ -38,6 +43,8 @@ int num_sms() {
 }  // namespace vitk
 
 extern "C" VITK_API int vitk_version(void) { return VITK_VERSION; }
+
+extern "C" VITK_API int64_t vitk_launch_count(void) { return vitk::g_launches.load(std::memory_order_relaxed); }
 
 extern "C" VITK_API const char* vitk_last_error(void) { return vitk::g_err; }
 

@@ -12,6 +12,7 @@ namespace vitk {
 int set_error(int code, const char* fmt, ...);   // stores the message, returns code
 int cuda_error(cudaError_t e, const char* what); // returns (int)e after storing the message
 int num_sms();                                   // SM count of the current device (cached)
+void count_launch();                             // bumps the process-wide kernel launch counter
 
 #define VITK_REQUIRE(cond, code, ...)                         \
   do {                                                        \
@@ -26,6 +27,7 @@ int num_sms();                                   // SM count of the current devi
 
 #define VITK_LAUNCH_CHECK(name)                                     \
   do {                                                              \
+    ::vitk::count_launch();                                         \
     cudaError_t _e = cudaGetLastError();                            \
     if (_e != cudaSuccess) return ::vitk::cuda_error(_e, name);     \
   } while (0)

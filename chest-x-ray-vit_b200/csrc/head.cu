@@ -1,6 +1,8 @@
 // Classifier head fused with the loss: final LayerNorm on the CLS rows → Linear(D→C) →
-// BCEWithLogits (mean) → all gradients of that chain.  Latency-bound (B rows of D floats);
-// one CTA per image.  Replaces HF modeling_vit.py:455,641-646 + loss_utils.py:110-112.
+// BCEWithLogits (mean) and the gradient of the loss w.r.t. the logits in ONE forward kernel;
+// the backward kernel chains that gradient through the classifier and the LayerNorm of the
+// B CLS rows.  Latency-bound (B rows of D floats); one CTA per image.
+// Replaces HF modeling_vit.py:455,641-646 + loss_utils.py:110-112.
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -24,17 +26,13 @@ __device__ __forceinline__ float block_sum(float v, float* scratch) {
 }
 
 __global__ void __launch_bounds__(kHeadThreads)
-head_bce_kernel(const float* __restrict__ h, int B, int T, int D, int C, const float* __restrict__ gamma,
+head_fwd_kernel(const float* __restrict__ h, int B, int T, int D, int C, const float* __restrict__ gamma,
                 const float* __restrict__ beta, float eps, const float* __restrict__ Wc, const float* __restrict__ bc,
-                const float* __restrict__ labels, float loss_scale, float* __restrict__ logits, float* __restrict__ loss,
-                __nv_bfloat16* __restrict__ dh, float* __restrict__ dWc, float* __restrict__ dbc,
-                float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  extern __shared__ float sm[];
-  float* xh = sm;          // [D] normalised row x̂
-  float* z = sm + D;       // [D] LN output
+                const float* __restrict__ labels, float* __restrict__ logits, float* __restrict__ loss,
+                float* __restrict__ dlogits, float* __restrict__ mean, float* __restrict__ rstd) {
+  extern __shared__ float z[];  // [D] LN output of this CLS row
   __shared__ float scratch[kHeadThreads / 32];
   __shared__ float s_logit[kMaxLabels];
-  __shared__ float s_dl[kMaxLabels];
   const int b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* x = h + static_cast<long long>(b) * T * D;  // CLS row
@@ -45,11 +43,11 @@ head_bce_kernel(const float* __restrict__ h, int B, int T, int D, int C, const f
   float q = 0.f;
   for (int d = tid; d < D; d += kHeadThreads) { const float c = x[d] - mu; q += c * c; }
   const float r = rsqrtf(block_sum(q, scratch) / D + eps);
-  for (int d = tid; d < D; d += kHeadThreads) {
-    const float n = (x[d] - mu) * r;
-    xh[d] = n;
-    z[d] = n * gamma[d] + beta[d];
+  if (tid == 0) {
+    if (mean) mean[b] = mu;
+    if (rstd) rstd[b] = r;
   }
+  for (int d = tid; d < D; d += kHeadThreads) z[d] = (x[d] - mu) * r * gamma[d] + beta[d];
   __syncthreads();
   for (int c = warp; c < C; c += kHeadThreads / 32) {
     float acc = 0.f;
@@ -64,60 +62,96 @@ head_bce_kernel(const float* __restrict__ h, int B, int T, int D, int C, const f
   }
   __syncthreads();
   if (labels == nullptr) return;
-  const float inv = loss_scale / (static_cast<float>(B) * C);
+  const float inv = 1.0f / (static_cast<float>(B) * C);
+  float li = 0.f;
   if (tid < C) {
     const float l = s_logit[tid], y = labels[b * C + tid];
     // max(l,0) − l·y + log1p(exp(−|l|)): the numerically stable form ATen uses
-    const float li = fmaxf(l, 0.f) - l * y + log1pf(expf(-fabsf(l)));
-    atomicAdd(loss, li / (static_cast<float>(B) * C));
-    const float sig = 1.0f / (1.0f + expf(-l));
-    s_dl[tid] = (sig - y) * inv;
+    li = (fmaxf(l, 0.f) - l * y + log1pf(expf(-fabsf(l)))) * inv;
+    if (dlogits) dlogits[b * C + tid] = (1.0f / (1.0f + expf(-l)) - y) * inv;
+  }
+  li = block_sum(li, scratch);
+  if (tid == 0) atomicAdd(loss, li);
+}
+
+__global__ void __launch_bounds__(kHeadThreads)
+head_bwd_kernel(const float* __restrict__ h, const float* __restrict__ mean, const float* __restrict__ rstd,
+                const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ Wc, int B,
+                int T, int D, int C, const float* __restrict__ dlogits, const float* __restrict__ dloss,
+                __nv_bfloat16* __restrict__ dh, float* __restrict__ dWc, float* __restrict__ dbc,
+                float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  extern __shared__ float sm[];
+  float* xh = sm;      // [D]
+  float* gz = sm + D;  // [D]
+  __shared__ float scratch[kHeadThreads / 32];
+  __shared__ float s_dl[kMaxLabels];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const float* x = h + static_cast<long long>(b) * T * D;
+  const float mu = mean[b], r = rstd[b];
+  const float gs = dloss ? *dloss : 1.0f;
+  if (tid < C) {
+    const float dl = dlogits[b * C + tid] * gs;
+    s_dl[tid] = dl;
+    atomicAdd(dbc + tid, dl);
   }
   __syncthreads();
-  if (dh == nullptr) return;
-  if (tid < C) atomicAdd(dbc + tid, s_dl[tid]);
-  // dz, dWc, then LayerNorm backward on this single row
   float s1 = 0.f, s2 = 0.f;
   for (int d = tid; d < D; d += kHeadThreads) {
+    const float n = (x[d] - mu) * r;
+    const float zd = n * gamma[d] + beta[d];
     float dz = 0.f;
-    const float zd = z[d];
     for (int c = 0; c < C; ++c) {
       const float dl = s_dl[c];
       dz += dl * Wc[static_cast<long long>(c) * D + d];
       atomicAdd(dWc + static_cast<long long>(c) * D + d, dl * zd);
     }
-    atomicAdd(dgamma + d, dz * xh[d]);
+    atomicAdd(dgamma + d, dz * n);
     atomicAdd(dbeta + d, dz);
     const float g = dz * gamma[d];
-    z[d] = g;  // reuse: own element only
+    xh[d] = n;
+    gz[d] = g;
     s1 += g;
-    s2 += g * xh[d];
+    s2 += g * n;
   }
   const float m1 = block_sum(s1, scratch) / D;
   const float m2 = block_sum(s2, scratch) / D;
   __nv_bfloat16* o = dh + static_cast<long long>(b) * T * D;
-  for (int d = tid; d < D; d += kHeadThreads) o[d] = __float2bfloat16_rn(r * (z[d] - m1 - xh[d] * m2));
+  for (int d = tid; d < D; d += kHeadThreads) o[d] = __float2bfloat16_rn(r * (gz[d] - m1 - xh[d] * m2));
 }
 
 }  // namespace vitk
 
 using namespace vitk;
 
-extern "C" VITK_API int vitk_head_bce(const float* h, int64_t B, int64_t T, int64_t D, int64_t C, const float* gamma,
-                             const float* beta, float eps, const float* Wc, const float* bc, const float* labels,
-                             float loss_scale, float* logits, float* loss, void* dh, float* dWc, float* dbc,
-                             float* dgamma, float* dbeta, vitk_stream_t stream) {
-  VITK_REQUIRE(h && gamma && beta && Wc && bc && logits, VITK_EINVAL, "head_bce: NULL argument");
+extern "C" VITK_API int vitk_head_fwd(const float* h, int64_t B, int64_t T, int64_t D, int64_t C, const float* gamma,
+                                      const float* beta, float eps, const float* Wc, const float* bc,
+                                      const float* labels, float* logits, float* loss, float* dlogits, float* mean,
+                                      float* rstd, vitk_stream_t stream) {
+  VITK_REQUIRE(h && gamma && beta && Wc && bc && logits, VITK_EINVAL, "head_fwd: NULL argument");
   VITK_REQUIRE(B > 0 && T > 0 && D > 0 && C > 0 && C <= kMaxLabels && D <= 8192, VITK_EINVAL,
-               "head_bce: unsupported shape B=%lld T=%lld D=%lld C=%lld", (long long)B, (long long)T, (long long)D,
+               "head_fwd: unsupported shape B=%lld T=%lld D=%lld C=%lld", (long long)B, (long long)T, (long long)D,
                (long long)C);
-  if (labels) VITK_REQUIRE(loss != nullptr, VITK_EINVAL, "head_bce: labels given but loss is NULL");
-  if (labels && dh) VITK_REQUIRE(dWc && dbc && dgamma && dbeta, VITK_EINVAL, "head_bce: gradient outputs missing");
+  if (labels) VITK_REQUIRE(loss != nullptr, VITK_EINVAL, "head_fwd: labels given but loss is NULL");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (labels) VITK_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), s));
-  head_bce_kernel<<<static_cast<unsigned>(B), kHeadThreads, 2 * D * sizeof(float), s>>>(
-      h, (int)B, (int)T, (int)D, (int)C, gamma, beta, eps, Wc, bc, labels, loss_scale, logits, loss,
-      static_cast<__nv_bfloat16*>(dh), dWc, dbc, dgamma, dbeta);
-  VITK_LAUNCH_CHECK("head_bce_kernel");
+  head_fwd_kernel<<<static_cast<unsigned>(B), kHeadThreads, D * sizeof(float), s>>>(
+      h, (int)B, (int)T, (int)D, (int)C, gamma, beta, eps, Wc, bc, labels, logits, loss, dlogits, mean, rstd);
+  VITK_LAUNCH_CHECK("head_fwd_kernel");
+  return 0;
+}
+
+extern "C" VITK_API int vitk_head_bwd(const float* h, const float* mean, const float* rstd, const float* gamma,
+                                      const float* beta, const float* Wc, int64_t B, int64_t T, int64_t D, int64_t C,
+                                      const float* dlogits, const float* dloss, void* dh, float* dWc, float* dbc,
+                                      float* dgamma, float* dbeta, vitk_stream_t stream) {
+  VITK_REQUIRE(h && mean && rstd && gamma && beta && Wc && dlogits && dh && dWc && dbc && dgamma && dbeta, VITK_EINVAL,
+               "head_bwd: NULL argument");
+  VITK_REQUIRE(B > 0 && T > 0 && D > 0 && C > 0 && C <= kMaxLabels && D <= 8192, VITK_EINVAL,
+               "head_bwd: unsupported shape B=%lld T=%lld D=%lld C=%lld", (long long)B, (long long)T, (long long)D,
+               (long long)C);
+  head_bwd_kernel<<<static_cast<unsigned>(B), kHeadThreads, 2 * D * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+      h, mean, rstd, gamma, beta, Wc, (int)B, (int)T, (int)D, (int)C, dlogits, dloss, static_cast<__nv_bfloat16*>(dh),
+      dWc, dbc, dgamma, dbeta);
+  VITK_LAUNCH_CHECK("head_bwd_kernel");
   return 0;
 }

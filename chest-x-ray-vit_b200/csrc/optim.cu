@@ -1,0 +1,105 @@
+// Multi-tensor-free optimizer step: parameters, gradients and both AdamW moments live in flat
+// fp32 buffers, so one HBM-bound kernel updates all of them and refreshes the bf16 shadow the
+// GEMMs read.  Follows torch.optim.AdamW (decoupled weight decay) as configured by HF Trainer
+// (HF trainer.py:1143-1217, training_args.py:778-862); global-norm clipping (HF trainer.py:2489-2493)
+// is a device-side scale factor so the step never synchronises with the host.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace vitk {
+
+__global__ void __launch_bounds__(256)
+adamw_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m, float4* __restrict__ v,
+             uint2* __restrict__ p16, long long n4, float lr, float b1, float b2, float eps, float wd, float bc1,
+             float rsqrt_bc2, const float* __restrict__ grad_scale) {
+  const float gs = grad_scale ? __ldg(grad_scale) : 1.0f;
+  const float step = lr / bc1, decay = 1.0f - lr * wd;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float4 pp = p[i], mm = m[i], vv = v[i];
+    const float4 gg = g[i];
+    float* pa = &pp.x; float* ma = &mm.x; float* va = &vv.x;
+    const float* ga = &gg.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float gr = ga[k] * gs;
+      ma[k] = fmaf(1.0f - b1, gr - ma[k], ma[k]);
+      va[k] = fmaf(1.0f - b2, gr * gr - va[k], va[k]);
+      const float denom = fmaf(sqrtf(va[k]), rsqrt_bc2, eps);
+      pa[k] = fmaf(-step, __fdiv_rn(ma[k], denom), pa[k] * decay);
+    }
+    p[i] = pp; m[i] = mm; v[i] = vv;
+    if (p16) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(pp.x, pp.y), hi = __floats2bfloat162_rn(pp.z, pp.w);
+      p16[i] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) sumsq_kernel(const float4* __restrict__ x, long long n4, float* __restrict__ out) {
+  __shared__ float red[8];
+  float s = 0.f;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 a = __ldg(x + i);
+    s += (a.x * a.x + a.y * a.y) + (a.z * a.z + a.w * a.w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    atomicAdd(out, t);
+  }
+}
+
+// torch.nn.utils.clip_grad_norm_: coef = min(1, max_norm / (‖g‖ + 1e-6))
+__global__ void clip_scale_kernel(const float* sumsq, float max_norm, float* scale) {
+  const float c = max_norm / (sqrtf(*sumsq) + 1e-6f);
+  *scale = c < 1.0f ? c : 1.0f;
+}
+
+}  // namespace vitk
+
+using namespace vitk;
+
+extern "C" VITK_API int vitk_adamw(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, float lr,
+                                   float beta1, float beta2, float eps, float weight_decay, float bias_corr1,
+                                   float bias_corr2, const float* grad_scale, vitk_stream_t stream) {
+  VITK_REQUIRE(p && g && m && v && n > 0 && n % 4 == 0, VITK_EINVAL, "adamw: n must be a positive multiple of 4");
+  VITK_REQUIRE(aligned16(p) && aligned16(g) && aligned16(m) && aligned16(v) && (reinterpret_cast<uintptr_t>(p_bf16) & 7) == 0,
+               VITK_EALIGN, "adamw: buffers must be 16-byte aligned");
+  VITK_REQUIRE(bias_corr1 > 0.f && bias_corr2 > 0.f, VITK_EINVAL, "adamw: bias corrections must be positive");
+  const long long n4 = n / 4;
+  long long blocks = (n4 + 255) / 256;
+  const long long cap = static_cast<long long>(num_sms()) * 8;
+  if (blocks > cap) blocks = cap;
+  adamw_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<float4*>(p), reinterpret_cast<const float4*>(g), reinterpret_cast<float4*>(m),
+      reinterpret_cast<float4*>(v), static_cast<uint2*>(p_bf16), n4, lr, beta1, beta2, eps, weight_decay, bias_corr1,
+      1.0f / sqrtf(bias_corr2), grad_scale);
+  VITK_LAUNCH_CHECK("adamw_kernel");
+  return 0;
+}
+
+extern "C" VITK_API int vitk_sumsq_f32(const float* x, int64_t n, float* out, vitk_stream_t stream) {
+  VITK_REQUIRE(x && out && n > 0 && n % 4 == 0 && aligned16(x), VITK_EINVAL, "sumsq: n must be a positive multiple of 4");
+  const long long n4 = n / 4;
+  long long blocks = (n4 + 255) / 256;
+  const long long cap = static_cast<long long>(num_sms()) * 8;
+  if (blocks > cap) blocks = cap;
+  sumsq_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float4*>(x), n4, out);
+  VITK_LAUNCH_CHECK("sumsq_kernel");
+  return 0;
+}
+
+extern "C" VITK_API int vitk_clip_scale(const float* sumsq, float max_norm, float* scale, vitk_stream_t stream) {
+  VITK_REQUIRE(sumsq && scale && max_norm > 0.f, VITK_EINVAL, "clip_scale: bad argument");
+  clip_scale_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(sumsq, max_norm, scale);
+  VITK_LAUNCH_CHECK("clip_scale_kernel");
+  return 0;
+}

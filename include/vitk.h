@@ -133,21 +133,44 @@ VITK_API int vitk_embed_bwd(const void* dh_bf16, int64_t B, int64_t T, int64_t D
 
 /* ------------------------------------------------------------------ head + loss
  * Replaces final LayerNorm on the CLS rows, classifier Linear(D→C) and BCEWithLogitsLoss (mean)
- * with their gradients (HF:455,641-646; loss_utils.py:110-112).
- *   h f32 [B,T,D] (only rows t=0 are read); labels f32 [B,C] or NULL (then no loss/backward).
- *   outputs: logits f32 [B,C]; loss f32 [1]; when labels != NULL and dh != NULL:
- *   dh bf16 [B,T,D] rows t=0 = gradient, (all other rows are NOT touched — zero them once);
- *   dWc [C,D], dbc [C], dgamma [D], dbeta [D] are ACCUMULATED.  loss_scale multiplies dlogits
- *   (1.0 for a plain mean over B*C). */
-VITK_API int vitk_head_bce(const float* h, int64_t B, int64_t T, int64_t D, int64_t C, const float* gamma, const float* beta,
-                  float eps, const float* Wc, const float* bc, const float* labels, float loss_scale, float* logits,
-                  float* loss, void* dh_bf16, float* dWc, float* dbc, float* dgamma, float* dbeta,
+ * with their gradients (HF:455,641-646; loss_utils.py:110-112; Trainer call site trainer.py:1978).
+ * vitk_head_fwd:  h f32 [B,T,D] (only rows t=0 are read) → logits f32 [B,C]; when labels f32
+ *   [B,C] != NULL also loss f32 [1] (mean over B·C) and, when dlogits != NULL, the fused loss
+ *   gradient dlogits f32 [B,C] = (σ(logit) − y)/(B·C).  mean/rstd f32 [B] (optional) are the
+ *   LayerNorm statistics the backward reuses. */
+VITK_API int vitk_head_fwd(const float* h, int64_t B, int64_t T, int64_t D, int64_t C, const float* gamma,
+                  const float* beta, float eps, const float* Wc, const float* bc, const float* labels, float* logits,
+                  float* loss, float* dlogits, float* mean, float* rstd, vitk_stream_t stream);
+/* vitk_head_bwd: chains dlogits·(*dloss) (dloss = device pointer to the upstream scalar gradient,
+ *   NULL = 1) through the classifier and the LayerNorm of the CLS rows.  dh bf16 [B,T,D]: rows
+ *   t=0 are written, all other rows are NOT touched (their gradient is zero — clear them once).
+ *   dWc [C,D], dbc [C], dgamma [D], dbeta [D] are ACCUMULATED (+=). */
+VITK_API int vitk_head_bwd(const float* h, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                  const float* Wc, int64_t B, int64_t T, int64_t D, int64_t C, const float* dlogits,
+                  const float* dloss, void* dh_bf16, float* dWc, float* dbc, float* dgamma, float* dbeta,
                   vitk_stream_t stream);
+
+/* ------------------------------------------------------------------ optimizer (flat buffers)
+ * torch.optim.AdamW semantics as HF Trainer configures it (trainer.py:1143-1217,1760):
+ *   g' = g·(*grad_scale)   (grad_scale: device pointer, NULL = 1; see vitk_clip_scale)
+ *   p ← p·(1 − lr·wd);  m ← m + (1−β1)(g' − m);  v ← v + (1−β2)(g'² − v);
+ *   p ← p − lr/bias_corr1 · m / (√v/√bias_corr2 + eps);   p_bf16 ← bf16(p) when p_bf16 != NULL.
+ * n multiple of 4; all buffers 16-byte aligned. */
+VITK_API int vitk_adamw(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, float lr, float beta1,
+               float beta2, float eps, float weight_decay, float bias_corr1, float bias_corr2,
+               const float* grad_scale, vitk_stream_t stream);
+/* out[0] += Σ x²  (global gradient norm, trainer.py:2489-2493). */
+VITK_API int vitk_sumsq_f32(const float* x, int64_t n, float* out, vitk_stream_t stream);
+/* scale[0] = min(1, max_norm / (sqrt(sumsq[0]) + 1e-6))  (torch.nn.utils.clip_grad_norm_). */
+VITK_API int vitk_clip_scale(const float* sumsq, float max_norm, float* scale, vitk_stream_t stream);
 
 /* ------------------------------------------------------------------ parameter shadow / misc
  * bf16 shadow refresh after optimizer.step(): dst_bf16[i] = bf16(src[i]). n multiple of 8. */
 VITK_API int vitk_cast_f32_bf16(const float* src, void* dst_bf16, int64_t n, vitk_stream_t stream);
 VITK_API int vitk_fill_zero(void* ptr, size_t bytes, vitk_stream_t stream);
+/* Number of kernels this library has launched in this process (all threads); bench.py reads it
+ * around the timed region to report gpu_launches. */
+VITK_API int64_t vitk_launch_count(void);
 
 #ifdef __cplusplus
 }
