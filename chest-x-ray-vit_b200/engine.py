@@ -1,0 +1,332 @@
+"""Sequencer of the hot path: owns the activation arena for a batch size and replays a
+pre-built list of C-ABI kernel launches for forward and backward (SURVEY.md §3.2/§3.3 give the
+HF call order this follows: modeling_vit.py:100-128 embeddings, :328-346 per layer, :455 final
+LayerNorm, :641-646 head + loss; backward is the reverse autograd order of §3.3).
+
+Data layout in HBM (per-GPU batch B, T tokens, D hidden, F intermediate, M = B·T):
+  residual stream ........ fp32 [M, D]   (h before every layer, h1 after attention)
+  GEMM operands .......... bf16 [M, D|3D|F] row-major (K contiguous for forward/dgrad; the same
+                           buffers are read "MN-major" by the wgrad GEMMs, no transposes)
+  fused QKV .............. bf16 [B, T, 3, H, 64] = [M, 3D]   (attention reads it in place)
+  weights ................ fp32 masters in one flat buffer + bf16 shadow of the GEMM weights
+  gradients .............. one flat fp32 buffer (param.grad are views); wgrad GEMMs accumulate
+                           into it with red.global.add, so split-K needs no workspace.
+Nothing here allocates per step: every launch argument is fixed when the arena is built, which
+is also what makes the whole step capturable in a CUDA graph.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, Dict, List, Optional, Tuple
+
+import torch
+
+from . import _lib, ops
+from ._lib import (EPI_ACCUM_F32, EPI_BIAS_BF16, EPI_BIAS_GELU_BF16, EPI_BIAS_RESID_F32, EPI_DGELU_BF16, EPI_PATCH_F32,
+                   EPI_STORE_BF16, GemmArgs)
+
+bf16, f32 = torch.bfloat16, torch.float32
+
+
+class _Plan:
+    """A list of (cfunc, args) launches; ``run`` appends the stream and checks return codes."""
+
+    def __init__(self):
+        self.steps: List[Tuple[object, tuple, str]] = []
+        self.gemm_flops: Dict[int, float] = {}      # step index → 2·M·N·K (bench.py's roofline leg)
+        self._keep = []      # keeps GemmArgs structs alive
+
+    def add(self, name: str, *args):
+        self.steps.append((getattr(_lib.lib(), name), args, name))
+
+    def gemm(self, a, b, M, N, K, d, epilogue, a_mn=False, b_mn=False, d2=None, bias=None, aux=None, rows_in=0,
+             rows_out=0, row_off=0, ldd=None, ld_aux=None, split_k=0, tile_n=0):
+        g = GemmArgs()
+        g.a, g.b, g.M, g.N, g.K = a.data_ptr(), b.data_ptr(), M, N, K
+        g.lda, g.ldb = a.stride(0), b.stride(0)
+        g.a_mn_major, g.b_mn_major, g.epilogue, g.split_k = int(a_mn), int(b_mn), epilogue, split_k
+        g.d, g.ldd = d.data_ptr(), (ldd if ldd is not None else d.stride(0))
+        g.d2 = None if d2 is None else d2.data_ptr()
+        g.bias = None if bias is None else bias.data_ptr()
+        g.aux = None if aux is None else aux.data_ptr()
+        g.ld_aux = (ld_aux if ld_aux is not None else (aux.stride(0) if aux is not None else 0))
+        g.rows_in, g.rows_out, g.row_off, g.tile_n, g.max_ctas = rows_in, rows_out, row_off, tile_n, 0
+        self._keep.append(g)
+        self.gemm_flops[len(self.steps)] = 2.0 * M * N * K
+        self.steps.append((_lib.lib().vitk_gemm_bf16, (C.byref(g),), "vitk_gemm_bf16"))
+
+    def call(self, fn: Callable[[], None]):
+        self.steps.append((None, (fn,), "python"))
+
+    def run(self, stream: int):
+        for fn, args, name in self.steps:
+            if fn is None:
+                args[0]()
+                continue
+            rc = fn(*args, stream)
+            if rc != 0:
+                _lib.check(rc, name)
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+class Arena:
+    """Activation + scratch buffers and launch plans for one (batch size, training?) pair."""
+
+    def __init__(self, eng: "Engine", B: int, train: bool):
+        cfg = eng.cfg
+        dev = eng.dev
+        D, Fi, H, L, Cn = cfg.hidden_size, cfg.intermediate_size, cfg.num_attention_heads, cfg.num_hidden_layers, cfg.num_labels
+        T, P = cfg.seq_len, cfg.num_patches
+        M = B * T
+        self.B, self.train, self.M = B, train, M
+        self.ticket = -1
+
+        def new(shape, dt):
+            return torch.empty(shape, dtype=dt, device=dev)
+
+        nl = L if train else 1                     # inference reuses one layer's worth of buffers
+        self.apatch = new((B * P, 768), bf16)
+        self.h = [new((M, D), f32) for _ in range(L + 1 if train else 1)]
+        self.h1 = [new((M, D), f32) for _ in range(nl)] if train else self.h
+        self.n1 = [new((M, D), bf16) for _ in range(nl)]
+        self.n2 = [new((M, D), bf16) for _ in range(nl)] if train else self.n1
+        self.st = [new((4, M), f32) for _ in range(nl)]          # mean1, rstd1, mean2, rstd2
+        self.qkv = [new((M, 3 * D), bf16) for _ in range(nl)]
+        self.o = [new((M, D), bf16) for _ in range(nl)]
+        self.lse = [new((B, H, T), f32) for _ in range(nl)]
+        self.u = [new((M, Fi), bf16) for _ in range(nl)]
+        self.a = [new((M, Fi), bf16) for _ in range(nl)]
+        self.labels = new((B, Cn), f32)
+        self.logits = new((B, Cn), f32)
+        self.loss = new((1,), f32)
+        self.dlogits = new((B, Cn), f32)
+        self.hstat = new((2, B), f32)
+        self.fwd = self._build_forward(eng, with_labels=False)
+        self.fwd_loss = self._build_forward(eng, with_labels=True)
+        if train:
+            self.dh = [new((M, D), bf16) for _ in range(2)]
+            self.dn = new((M, D), bf16)
+            self.du = new((M, Fi), bf16)
+            self.do = new((M, D), bf16)
+            self.dqkv = new((M, 3 * D), bf16)
+            self.attn_ws = new((ops.attn_bwd_workspace_bytes(B, T, H),), torch.uint8)
+            self.dpatch = new((B * P, D), bf16)
+            self.dloss = new((1,), f32)
+            self.dlogits_in = new((B, Cn), f32)
+            self.bwd_loss = self._build_backward(eng, from_loss=True)
+            self.bwd_logits = self._build_backward(eng, from_loss=False)
+
+    # ------------------------------------------------------------------ forward plan
+    def _build_forward(self, eng: "Engine", with_labels: bool) -> _Plan:
+        cfg, w = eng.cfg, eng.w
+        D, Fi, H, L, Cn = cfg.hidden_size, cfg.intermediate_size, cfg.num_attention_heads, cfg.num_hidden_layers, cfg.num_labels
+        T, P, B, M = cfg.seq_len, cfg.num_patches, self.B, self.M
+        eps = cfg.layer_norm_eps
+        scale = 64 ** -0.5
+        pl = _Plan()
+        h0 = self.h[0]
+        pl.add("vitk_embed_cls", _p(w["cls"]), _p(w["pos"]), B, T, D, _p(h0))
+        pl.gemm(self.apatch, w["wp16"], B * P, D, 768, h0, EPI_PATCH_F32, bias=w["bp"], aux=w["pos"], rows_in=P, rows_out=T,
+                row_off=1, ldd=D, ld_aux=D)
+        for l in range(L):
+            i = l if self.train else 0
+            hin = self.h[l] if self.train else self.h[0]
+            h1 = self.h1[i] if self.train else self.h[0]
+            hout = self.h[l + 1] if self.train else self.h[0]
+            lw = w["layers"][l]
+            st = self.st[i]
+            pl.add("vitk_layernorm_fwd", _p(hin), D, _p(lw["g1"]), _p(lw["b1"]), eps, M, D, _p(self.n1[i]), _p(st[0]), _p(st[1]))
+            pl.gemm(self.n1[i], lw["wqkv16"], M, 3 * D, D, self.qkv[i], EPI_BIAS_BF16, bias=lw["bqkv"])
+            pl.add("vitk_attn_fwd", _p(self.qkv[i]), B, T, H, scale, _p(self.o[i]), _p(self.lse[i]))
+            pl.gemm(self.o[i], lw["wo16"], M, D, D, h1, EPI_BIAS_RESID_F32, bias=lw["bo"], aux=hin)
+            pl.add("vitk_layernorm_fwd", _p(h1), D, _p(lw["g2"]), _p(lw["b2"]), eps, M, D, _p(self.n2[i]), _p(st[2]), _p(st[3]))
+            pl.gemm(self.n2[i], lw["w1_16"], M, Fi, D, self.u[i], EPI_BIAS_GELU_BF16, d2=self.a[i], bias=lw["bf1"])
+            pl.gemm(self.a[i], lw["w2_16"], M, D, Fi, hout, EPI_BIAS_RESID_F32, bias=lw["bf2"], aux=h1)
+        hl = self.h[L] if self.train else self.h[0]
+        self.h_last = hl
+        if with_labels:
+            pl.add("vitk_head_fwd", _p(hl), B, T, D, Cn, _p(w["gf"]), _p(w["bf"]), eps, _p(w["wc"]), _p(w["bc"]), _p(self.labels),
+                   _p(self.logits), _p(self.loss), _p(self.dlogits), _p(self.hstat[0]), _p(self.hstat[1]))
+        else:
+            pl.add("vitk_head_fwd", _p(hl), B, T, D, Cn, _p(w["gf"]), _p(w["bf"]), eps, _p(w["wc"]), _p(w["bc"]), None,
+                   _p(self.logits), None, None, _p(self.hstat[0]), _p(self.hstat[1]))
+        return pl
+
+    # ------------------------------------------------------------------ backward plan
+    def _build_backward(self, eng: "Engine", from_loss: bool) -> _Plan:
+        cfg, w, g = eng.cfg, eng.w, eng.g
+        D, Fi, H, L, Cn = cfg.hidden_size, cfg.intermediate_size, cfg.num_attention_heads, cfg.num_hidden_layers, cfg.num_labels
+        T, P, B, M = cfg.seq_len, cfg.num_patches, self.B, self.M
+        scale = 64 ** -0.5
+        pl = _Plan()
+        dh, dh1 = self.dh
+        pl.add("vitk_fill_zero", _p(dh), dh.numel() * 2)
+        pl.add("vitk_head_bwd", _p(self.h_last), _p(self.hstat[0]), _p(self.hstat[1]), _p(w["gf"]), _p(w["bf"]), _p(w["wc"]),
+               B, T, D, Cn, _p(self.dlogits if from_loss else self.dlogits_in), _p(self.dloss) if from_loss else None,
+               _p(dh), _p(g["wc"]), _p(g["bc"]), _p(g["gf"]), _p(g["bf"]))
+        for l in reversed(range(L)):
+            lw, lg, st = w["layers"][l], g["layers"][l], self.st[l]
+            # MLP
+            pl.gemm(dh, self.a[l], D, Fi, M, lg["w2"], EPI_ACCUM_F32, a_mn=True, b_mn=True)
+            pl.add("vitk_colsum_bf16", _p(dh), M, D, D, _p(lg["bf2"]))
+            pl.gemm(dh, lw["w2_16"], M, Fi, D, self.du, EPI_DGELU_BF16, b_mn=True, aux=self.u[l])
+            pl.gemm(self.du, self.n2[l], Fi, D, M, lg["w1"], EPI_ACCUM_F32, a_mn=True, b_mn=True)
+            pl.add("vitk_colsum_bf16", _p(self.du), M, Fi, Fi, _p(lg["bf1"]))
+            pl.gemm(self.du, lw["w1_16"], M, D, Fi, self.dn, EPI_STORE_BF16, b_mn=True)
+            pl.add("vitk_layernorm_bwd", _p(self.dn), _p(self.h1[l]), D, _p(st[2]), _p(st[3]), _p(lw["g2"]), _p(dh), M, D,
+                   _p(dh1), _p(lg["g2"]), _p(lg["b2"]))
+            # attention
+            pl.gemm(dh1, self.o[l], D, D, M, lg["wo"], EPI_ACCUM_F32, a_mn=True, b_mn=True)
+            pl.add("vitk_colsum_bf16", _p(dh1), M, D, D, _p(lg["bo"]))
+            pl.gemm(dh1, lw["wo16"], M, D, D, self.do, EPI_STORE_BF16, b_mn=True)
+            pl.add("vitk_attn_bwd", _p(self.qkv[l]), _p(self.o[l]), _p(self.do), _p(self.lse[l]), B, T, H, scale,
+                   _p(self.dqkv), _p(self.attn_ws))
+            pl.gemm(self.dqkv, self.n1[l], 3 * D, D, M, lg["wqkv"], EPI_ACCUM_F32, a_mn=True, b_mn=True)
+            pl.add("vitk_colsum_bf16", _p(self.dqkv), M, 3 * D, 3 * D, _p(lg["bqkv"]))
+            pl.gemm(self.dqkv, lw["wqkv16"], M, D, 3 * D, self.dn, EPI_STORE_BF16, b_mn=True)
+            pl.add("vitk_layernorm_bwd", _p(self.dn), _p(self.h[l]), D, _p(st[0]), _p(st[1]), _p(lw["g1"]), _p(dh1), M, D,
+                   _p(dh), _p(lg["g1"]), _p(lg["b1"]))
+            pl.call(lambda l=l: eng._layer_grads_ready(l))
+        pl.add("vitk_embed_bwd", _p(dh), B, T, D, _p(g["pos"]), _p(g["cls"]), _p(g["bp"]), _p(self.dpatch))
+        pl.gemm(self.dpatch, self.apatch, D, 768, B * P, g["wp"], EPI_ACCUM_F32, a_mn=True, b_mn=True)
+        pl.call(lambda: eng._rest_grads_ready())
+        return pl
+
+
+class Engine:
+    def __init__(self, model):
+        self.model = model
+        self.cfg = model.config
+        self.dev = model.flat_parameters().device
+        self.ticket = 0
+        self.arenas: Dict[Tuple[int, bool], Arena] = {}
+        self.grad_sync = None            # parallel.GradSync, set by the caller for N>1
+        self.w = self._weight_views(model.flat_parameters(), model.shadow())
+        self.g = self._weight_views(model.flat_grads(), None)
+        self._grad_views = {n: model.layout.view(model.flat_grads(), n) for n in model.layout.names}
+        self._params = dict(model.named_parameters())
+
+    def _weight_views(self, flat: torch.Tensor, shadow: Optional[torch.Tensor]):
+        """Kernel-facing views of a flat buffer laid out by FlatLayout.  With ``shadow`` (bf16 copy
+        of the GEMM prefix) the matrix weights come from it under keys ending in ``16``."""
+        cfg, lay = self.cfg, self.model.layout
+        D, Fi = cfg.hidden_size, cfg.intermediate_size
+        want16 = shadow is not None
+
+        def v(name):
+            return lay.view(flat, name)
+
+        def v16(name, rows, cols):
+            o = lay.offset[name]
+            src = shadow if want16 else flat
+            return src[o:o + rows * cols].view(rows, cols)
+
+        def span(name, n):
+            o = lay.offset[name]
+            return flat[o:o + n]
+
+        sfx = "16" if want16 else ""
+        out = {"cls": v("vit.embeddings.cls_token").view(D), "pos": v("vit.embeddings.position_embeddings").view(-1, D),
+               "bp": v("vit.embeddings.patch_embeddings.projection.bias"),
+               "wp" + sfx: v16("vit.embeddings.patch_embeddings.projection.weight", D, 768),
+               "gf": v("vit.layernorm.weight"), "bf": v("vit.layernorm.bias"),
+               "wc": v("classifier.weight"), "bc": v("classifier.bias"), "layers": []}
+        for i in range(cfg.num_hidden_layers):
+            p = f"vit.encoder.layer.{i}."
+            out["layers"].append({
+                "wqkv" + sfx: v16(p + "attention.attention.query.weight", 3 * D, D),
+                "bqkv": span(p + "attention.attention.query.bias", 3 * D),
+                "wo" + sfx: v16(p + "attention.output.dense.weight", D, D), "bo": v(p + "attention.output.dense.bias"),
+                ("w1_16" if want16 else "w1"): v16(p + "intermediate.dense.weight", Fi, D), "bf1": v(p + "intermediate.dense.bias"),
+                ("w2_16" if want16 else "w2"): v16(p + "output.dense.weight", D, Fi), "bf2": v(p + "output.dense.bias"),
+                "g1": v(p + "layernorm_before.weight"), "b1": v(p + "layernorm_before.bias"),
+                "g2": v(p + "layernorm_after.weight"), "b2": v(p + "layernorm_after.bias")})
+        return out
+
+    def arena(self, B: int, train: bool) -> Arena:
+        key = (B, train)
+        a = self.arenas.get(key)
+        if a is None:
+            a = self.arenas[key] = Arena(self, B, train)
+        return a
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, pixel_values: torch.Tensor, labels: Optional[torch.Tensor], save: bool):
+        cfg = self.cfg
+        B = pixel_values.shape[0]
+        ar = self.arena(B, save)
+        if pixel_values.device != self.dev:
+            pixel_values = pixel_values.to(self.dev, non_blocking=True)
+        self.model.shadow()                                   # refresh bf16 weights if the masters moved
+        if pixel_values.dtype == torch.uint8:
+            x = pixel_values.reshape(B, cfg.image_size, cfg.image_size)
+            ops.patchify_u8(x if x.is_contiguous() else x.contiguous(), cfg.image_mean, cfg.image_std, out=ar.apatch)
+        else:
+            x = pixel_values if pixel_values.dtype == f32 else pixel_values.to(f32)     # HF:444-446 casts to the weight dtype
+            ops.patchify_f32(x if x.is_contiguous() else x.contiguous(), out=ar.apatch)
+        if labels is not None:
+            ar.labels.copy_(labels.reshape(B, cfg.num_labels), non_blocking=True)
+        (ar.fwd_loss if labels is not None else ar.fwd).run(torch.cuda.current_stream().cuda_stream)
+        if save:
+            self.ticket += 1
+            ar.ticket = self.ticket
+        loss = ar.loss[0].clone() if labels is not None else None
+        return loss, ar.logits.clone()
+
+    # ------------------------------------------------------------------ backward
+    def _bind_grads(self) -> None:
+        """Make every param.grad a view of the flat gradient buffer.  A grad that is None means a
+        fresh accumulation (zero it); a foreign tensor is folded in so ``+=`` semantics hold."""
+        flat = self.model.flat_grads()
+        fresh = 0
+        foreign = []
+        for n, p in self._params.items():
+            gv = self._grad_views[n]
+            if p.grad is None:
+                fresh += 1
+            elif p.grad.data_ptr() != gv.data_ptr():
+                foreign.append((n, p.grad))
+        if fresh == len(self._params):
+            ops.fill_zero(flat)
+        elif fresh:
+            for n, p in self._params.items():
+                if p.grad is None:
+                    self._grad_views[n].zero_()
+        for n, gt in foreign:
+            self._grad_views[n].copy_(gt)
+        if fresh or foreign:
+            for n, p in self._params.items():
+                p.grad = self._grad_views[n]
+
+    def backward(self, ticket: int, dloss: Optional[torch.Tensor], dlogits: Optional[torch.Tensor]) -> None:
+        ar = next((a for a in self.arenas.values() if a.train and a.ticket == ticket), None)
+        if ar is None:
+            raise RuntimeError("chest_x_ray_vit_b200: the activations of this forward were overwritten by a later "
+                               "forward with the same batch size; call backward() before the next forward()")
+        if dloss is None and dlogits is None:
+            return
+        self._bind_grads()
+        if self.grad_sync is not None:
+            self.grad_sync.begin(self.model)
+        stream = torch.cuda.current_stream().cuda_stream
+        if dloss is not None and dlogits is None:
+            ar.dloss.copy_(dloss.reshape(1), non_blocking=True)
+            ar.bwd_loss.run(stream)
+        else:
+            if dloss is not None:      # both the loss and the logits were used downstream
+                torch.add(dlogits.to(f32), ar.dlogits * dloss.to(f32), out=ar.dlogits_in)
+            else:
+                ar.dlogits_in.copy_(dlogits)
+            ar.bwd_logits.run(stream)
+        ar.ticket = -1
+
+    def _layer_grads_ready(self, l: int) -> None:
+        if self.grad_sync is not None:
+            self.grad_sync.layer_ready(l)
+
+    def _rest_grads_ready(self) -> None:
+        if self.grad_sync is not None:
+            self.grad_sync.rest_ready()

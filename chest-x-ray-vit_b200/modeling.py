@@ -207,6 +207,7 @@ class ViTForImageClassification(nn.Module):
         self._shadow_version = -1
         self._engine: Optional[Engine] = None
         self._pnames: List[str] = []
+        self._plist = None
         for name in self.layout.names:
             self._register(name, nn.Parameter(self.layout.view(flat, name)))
         self.reset_parameters()
@@ -217,7 +218,7 @@ class ViTForImageClassification(nn.Module):
         parts = name.split(".")
         for part in parts[:-1]:
             if not hasattr(mod, part):
-                mod.add_module(part, _Holder())
+                mod.add_module(part, nn.ModuleList() if part == "layer" else _Holder())
             mod = getattr(mod, part)
         mod.register_parameter(parts[-1], p)
         self._pnames.append(name)
@@ -274,14 +275,21 @@ class ViTForImageClassification(nn.Module):
         if self._flat_shadow is None:
             self._flat_shadow = torch.empty(self.layout.gemm_end, dtype=torch.bfloat16, device=flat.device)
             self._shadow_version = -1
-        if self._shadow_version != flat._version:
+        key = self._param_version()
+        if self._shadow_version != key:
             ops.cast_f32_bf16(flat[: self.layout.gemm_end], self._flat_shadow)
-            self._shadow_version = flat._version
+            self._shadow_version = key
         return self._flat_shadow
+
+    def _param_version(self) -> int:
+        # in-place updates (optimizer.step, load_state_dict, init) bump each parameter's counter
+        if self._plist is None:
+            self._plist = list(self.parameters())
+        return sum(p._version for p in self._plist)
 
     def mark_shadow_fresh(self) -> None:
         """Called by VitkAdamW, whose kernel rewrites the shadow together with the masters."""
-        self._shadow_version = self._flat_params._version
+        self._shadow_version = self._param_version()
 
     def engine(self) -> Engine:
         if self._engine is None:
@@ -329,7 +337,7 @@ class ViTForImageClassification(nn.Module):
             self.config.problem_type = "multi_label_classification"     # HF loss_utils.py:92-98 (float labels)
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
         if need_grad:
-            loss, logits = _VitFunction.apply(self, pixel_values, labels, self._flat_params)
+            loss, logits = _VitFunction.apply(self, pixel_values, labels, self.classifier.bias)
         else:
             loss, logits = eng.forward(pixel_values, labels, save=False)
         return ImageClassifierOutput(loss=loss if labels is not None else None, logits=logits)
@@ -338,10 +346,10 @@ class ViTForImageClassification(nn.Module):
 class _VitFunction(torch.autograd.Function):
     """One autograd node for the whole model: forward runs Engine.forward, backward runs
     Engine.backward, which accumulates fp32 gradients straight into ``param.grad`` (views of one
-    flat buffer).  ``flat`` is passed only so that autograd sees a differentiable input."""
+    flat buffer).  ``anchor`` (one parameter) is passed only so that autograd records the node."""
 
     @staticmethod
-    def forward(ctx, model: ViTForImageClassification, pixel_values, labels, flat):
+    def forward(ctx, model: ViTForImageClassification, pixel_values, labels, anchor):
         eng = model.engine()
         loss, logits = eng.forward(pixel_values, labels, save=True)
         ctx.model = model
