@@ -17,6 +17,8 @@ EPI_PATCH_F32 = 4
 EPI_DGELU_BF16 = 5
 EPI_ACCUM_F32 = 6
 EPI_STORE_F32 = 7
+EPI_BIAS_GELUG_BF16 = 8
+EPI_MUL_BF16 = 9
 
 
 class GemmArgs(C.Structure):
@@ -31,7 +33,7 @@ class GemmArgs(C.Structure):
         ("bias", C.c_void_p),
         ("aux", C.c_void_p), ("ld_aux", C.c_int64),
         ("rows_in", C.c_int64), ("rows_out", C.c_int64), ("row_off", C.c_int64),
-        ("tile_n", C.c_int32), ("max_ctas", C.c_int32),
+        ("tile_n", C.c_int32), ("max_ctas", C.c_int32), ("variant", C.c_int32),
     ]
 
 

@@ -21,11 +21,9 @@
 
 #include "common.cuh"
 #include "sm100_prims.cuh"
+#include "tmap.cuh"
 
 namespace vitk {
-
-int make_tensor_map_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                         const uint64_t* strides_bytes, const uint32_t* box);
 
 constexpr int kTile = 128;   // queries per CTA (fwd) / keys per CTA (bwd) / tokens per inner block
 constexpr int kDh = 64;

@@ -13,10 +13,11 @@
 #include <cuda.h>
 
 #include <mutex>
-#include <unordered_map>
 
 #include "common.cuh"
+#include "gemm_epilogue.cuh"
 #include "sm100_prims.cuh"
+#include "tmap.cuh"
 
 namespace vitk {
 
@@ -47,28 +48,6 @@ struct GemmParams {
   int rows_in, rows_out, row_off;
 };
 
-// ------------------------------------------------------------------------- math helpers
-// erf via Abramowitz–Stegun 7.1.26 (|err| < 2e-7 in fp32 with MUFU ex2/rcp): the exact-erf
-// GELU the reference uses (HF activations.py:85-86), evaluated in the epilogue.
-__device__ __forceinline__ float erf_as(float x) {
-  const float ax = fabsf(x);
-  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  poly *= t;
-  const float e = exp2f(-ax * ax * 1.4426950408889634f);
-  const float y = fmaf(-poly, e, 1.0f);
-  return copysignf(y, x);
-}
-__device__ __forceinline__ float gelu_erf(float u) { return 0.5f * u * (1.0f + erf_as(u * 0.7071067811865476f)); }
-__device__ __forceinline__ float gelu_erf_grad(float u) {
-  const float cdf = 0.5f * (1.0f + erf_as(u * 0.7071067811865476f));
-  const float pdf = 0.3989422804014327f * exp2f(-0.5f * u * u * 1.4426950408889634f);
-  return fmaf(u, pdf, cdf);
-}
-
 __device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float (&v)[32]) {
   uint4* o = reinterpret_cast<uint4*>(dst);
 #pragma unroll
@@ -86,7 +65,7 @@ __device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float (&
 __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int row, int col0, float (&v)[32]) {
   const int epi = p.epi;
   if (epi == VITK_EPI_BIAS_BF16 || epi == VITK_EPI_BIAS_GELU_BF16 || epi == VITK_EPI_BIAS_RESID_F32 ||
-      epi == VITK_EPI_PATCH_F32) {
+      epi == VITK_EPI_PATCH_F32 || epi == VITK_EPI_BIAS_GELUG_BF16) {
     if (p.bias != nullptr) {
       const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
 #pragma unroll
@@ -111,6 +90,19 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int row, int
       store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.d2) + off, v);
       break;
     }
+    case VITK_EPI_BIAS_GELUG_BF16: {
+      const long long off = static_cast<long long>(row) * p.ldd + col0;
+      float gr[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const GeluParts g = gelu_parts(v[i]);
+        gr[i] = fmaf(v[i], g.pdf, g.cdf);
+        v[i] *= g.cdf;
+      }
+      store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.d) + off, v);
+      if (p.d2 != nullptr) store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.d2) + off, gr);
+      break;
+    }
     case VITK_EPI_BIAS_RESID_F32:
     case VITK_EPI_PATCH_F32: {
       long long out_row = row, aux_row = row;
@@ -128,6 +120,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int row, int
       }
       break;
     }
+    case VITK_EPI_MUL_BF16:
     case VITK_EPI_DGELU_BF16: {
       const uint4* u4 = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.aux) +
                                                        static_cast<long long>(row) * p.ld_aux + col0);
@@ -138,8 +131,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int row, int
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
-          v[8 * i + 2 * j + 0] *= gelu_erf_grad(f.x);
-          v[8 * i + 2 * j + 1] *= gelu_erf_grad(f.y);
+          v[8 * i + 2 * j + 0] *= (epi == VITK_EPI_MUL_BF16) ? f.x : gelu_erf_grad(f.x);
+          v[8 * i + 2 * j + 1] *= (epi == VITK_EPI_MUL_BF16) ? f.y : gelu_erf_grad(f.y);
         }
       }
       store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.d) + static_cast<long long>(row) * p.ldd + col0, v);
@@ -324,40 +317,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 }
 
 // ------------------------------------------------------------------------- host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = [] {
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) != cudaSuccess ||
-        q != cudaDriverEntryPointSuccess)
-      ptr = nullptr;
-    return reinterpret_cast<EncodeTiledFn>(ptr);
-  }();
-  return fn;
-}
-
-// bf16 tensor map with 128-byte swizzle; dims/strides innermost first; rank 2 or 3.
-int make_tensor_map_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                         const uint64_t* strides_bytes /* rank-1 */, const uint32_t* box) {
-  EncodeTiledFn fn = encode_fn();
-  VITK_REQUIRE(fn != nullptr, VITK_EDRIVER, "cuTensorMapEncodeTiled not available from the driver");
-  cuuint64_t gdim[3];
-  cuuint64_t gstr[2];
-  cuuint32_t bx[3];
-  cuuint32_t es[3] = {1, 1, 1};
-  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; }
-  for (int i = 0; i < rank - 1; ++i) gstr[i] = strides_bytes[i];
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim,
-                  gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  VITK_REQUIRE(r == CUDA_SUCCESS, VITK_EDRIVER, "cuTensorMapEncodeTiled failed (CUresult %d)", static_cast<int>(r));
-  return 0;
-}
-
 template <int BN, bool A_MN, bool B_MN>
 static int launch_gemm(const vitk_gemm_args& a, const GemmParams& p, int grid, cudaStream_t stream) {
   using Cfg = TileCfg<BN>;
@@ -414,6 +373,8 @@ static int choose_tile_n(long long M, long long N, int sms) {
   return best;
 }
 
+int gemm2_try_launch(const vitk_gemm_args& a, cudaStream_t stream, bool* handled);   // gemm2.cu
+
 }  // namespace vitk
 
 using namespace vitk;
@@ -431,14 +392,18 @@ extern "C" VITK_API int vitk_gemm_bf16(const vitk_gemm_args* args, vitk_stream_t
   VITK_REQUIRE(a.lda % 8 == 0 && a.ldb % 8 == 0, VITK_EALIGN, "gemm: lda/ldb must be multiples of 8 elements");
   VITK_REQUIRE(a.lda >= (a.a_mn_major ? a.M : a.K) && a.ldb >= (a.b_mn_major ? a.N : a.K), VITK_EINVAL,
                "gemm: leading dimension smaller than the contiguous extent");
-  VITK_REQUIRE(a.epilogue >= 0 && a.epilogue <= VITK_EPI_STORE_F32, VITK_EINVAL, "gemm: unknown epilogue %d", a.epilogue);
+  VITK_REQUIRE(a.epilogue >= 0 && a.epilogue <= VITK_EPI_MUL_BF16, VITK_EINVAL, "gemm: unknown epilogue %d", a.epilogue);
   const bool f32_out = a.epilogue == VITK_EPI_BIAS_RESID_F32 || a.epilogue == VITK_EPI_PATCH_F32 ||
                        a.epilogue == VITK_EPI_ACCUM_F32 || a.epilogue == VITK_EPI_STORE_F32;
   VITK_REQUIRE(a.ldd % (f32_out ? 4 : 8) == 0 && a.ldd >= a.N, VITK_EALIGN, "gemm: ldd=%lld not aligned / too small",
                (long long)a.ldd);
   if (a.epilogue == VITK_EPI_BIAS_GELU_BF16)
     VITK_REQUIRE(a.d2 != nullptr && aligned16(a.d2), VITK_EINVAL, "gemm: BIAS_GELU needs d2");
-  if (a.epilogue == VITK_EPI_BIAS_RESID_F32 || a.epilogue == VITK_EPI_PATCH_F32 || a.epilogue == VITK_EPI_DGELU_BF16)
+  if (a.epilogue == VITK_EPI_BIAS_GELUG_BF16 && a.d2 != nullptr)
+    VITK_REQUIRE(aligned16(a.d2), VITK_EALIGN, "gemm: d2 must be 16-byte aligned");
+  VITK_REQUIRE(a.variant >= 0 && a.variant <= 2, VITK_EINVAL, "gemm: variant must be 0 (auto), 1 (single-CTA) or 2 (CTA pair)");
+  if (a.epilogue == VITK_EPI_BIAS_RESID_F32 || a.epilogue == VITK_EPI_PATCH_F32 || a.epilogue == VITK_EPI_DGELU_BF16 ||
+      a.epilogue == VITK_EPI_MUL_BF16)
     VITK_REQUIRE(a.aux != nullptr && aligned16(a.aux) && a.ld_aux % 8 == 0 && a.ld_aux >= a.N, VITK_EINVAL,
                  "gemm: epilogue %d needs aux with ld_aux >= N, multiple of 8", a.epilogue);
   if (a.epilogue == VITK_EPI_PATCH_F32)
@@ -447,6 +412,12 @@ extern "C" VITK_API int vitk_gemm_bf16(const vitk_gemm_args* args, vitk_stream_t
   if (a.bias) VITK_REQUIRE(aligned16(a.bias), VITK_EALIGN, "gemm: bias must be 16-byte aligned");
   VITK_REQUIRE(a.split_k >= 0 && (a.split_k <= 1 || a.epilogue == VITK_EPI_ACCUM_F32), VITK_EINVAL,
                "gemm: split_k > 1 requires VITK_EPI_ACCUM_F32");
+
+  {
+    bool handled = false;
+    const int rc = gemm2_try_launch(a, stream, &handled);
+    if (rc != 0 || handled) return rc;
+  }
 
   const int sms = num_sms();
   int bn = a.tile_n ? a.tile_n : choose_tile_n(a.M, a.N, sms);

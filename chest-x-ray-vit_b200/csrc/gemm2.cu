@@ -1,0 +1,528 @@
+// CTA-pair (cta_group::2) persistent bf16 GEMM for sm_100a — the main dense-contraction kernel.
+//
+// One cluster of two CTAs (two SMs of a TPC) owns a 256×BN output tile: each CTA stages its own
+// 128 rows of A and HALF of the B tile (BN/2 rows) with TMA, the leader CTA's single MMA thread
+// issues tcgen05.mma.cta_group::2 (M = 256) which reads both CTAs' shared memory, and each CTA
+// ends up with its 128 accumulator rows in its own TMEM.  Compared with the single-CTA kernel in
+// gemm.cu this halves the B traffic from L2 and the B reads from shared memory per FLOP.
+//
+//   warp 0        TMA producer (lane 0): A half + B half per 64-wide K block into a ring of stages;
+//                 both CTAs' loads complete on the LEADER's full barrier
+//   warp 1        TMEM allocation (both CTAs); in the leader, lane 0 issues the MMAs and commits to
+//                 the stage-empty barriers (multicast to both CTAs) and the accumulator-full barriers
+//   warps 2,3     idle (keep warp id % 4 of the epilogue warps aligned with their TMEM lane quadrant)
+//   warps 4..11   epilogue: TMEM → registers → fused math → 32×32 slab in swizzled smem → TMA store
+//                 (or TMA reduce-add for split-K wgrad); residual / multiplier tiles arrive by TMA
+//                 load into the same slab and are updated in place.  No per-thread global access:
+//                 every byte of C/D traffic is a full-line TMA transaction, M tails are clipped by TMA.
+//   accumulators  double-buffered in TMEM (2×BN columns) so the epilogue of tile i overlaps the MMAs
+//                 of tile i+1.
+#include <cuda.h>
+
+#include <mutex>
+
+#include "common.cuh"
+#include "gemm_epilogue.cuh"
+#include "sm100_prims.cuh"
+#include "tmap.cuh"
+
+namespace vitk {
+
+constexpr int k2BM = 128;            // rows per CTA (256 per pair)
+constexpr int k2BK = 64;
+constexpr int k2EpiWarps = 8;
+constexpr int k2FirstEpiWarp = 4;
+constexpr int k2Threads = (k2FirstEpiWarp + k2EpiWarps) * 32;   // 384
+constexpr int k2ABytes = k2BM * k2BK * 2;                       // 16 KB
+constexpr int k2SlabBytes = 12288;                              // per epilogue warp: 3×4 KB (f32) or 4×2 KB (bf16)
+constexpr int k2StagingBytes = k2EpiWarps * k2SlabBytes;        // 96 KB
+constexpr int k2BarBytes = 1024;
+
+template <int BN>
+struct Cfg2 {
+  static constexpr int kBHalfRows = BN / 2;
+  static constexpr int kBBytes = kBHalfRows * k2BK * 2;
+  static constexpr int kStageBytes = k2ABytes + kBBytes;
+  static constexpr int kStages = (BN == 128) ? 5 : 4;
+  static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;
+  static constexpr int kSmemBytes = kStages * kStageBytes + k2StagingBytes + k2BarBytes + 1024 /*align slack*/;
+};
+
+struct Gemm2Params {
+  int M, N, K;
+  int n_tiles, mn_tiles, k_splits, kb_per_split, kb_total, total_work;
+  int epi;
+  int has_d2;
+  const float* bias;
+};
+
+struct Work2 {
+  int m_blk, n_blk, kb_begin, kb_end;
+};
+__device__ __forceinline__ Work2 decode_work2(const Gemm2Params& p, int w) {
+  const int ks = w / p.mn_tiles;
+  const int t = w - ks * p.mn_tiles;
+  Work2 it;
+  it.m_blk = t / p.n_tiles;
+  it.n_blk = t - it.m_blk * p.n_tiles;
+  it.kb_begin = ks * p.kb_per_split;
+  it.kb_end = min(it.kb_begin + p.kb_per_split, p.kb_total);
+  return it;
+}
+
+// ------------------------------------------------------------------------- slab addressing
+// bf16 slab: 32 rows × 64 B, 64-byte swizzle (16-byte chunk j of row r lives at chunk j ^ ((r>>1)&3))
+__device__ __forceinline__ uint32_t slab16_off(int r, int j) { return r * 64 + ((j ^ ((r >> 1) & 3)) << 4); }
+// f32 slab: 32 rows × 128 B, 128-byte swizzle (chunk j of row r lives at chunk j ^ (r&7))
+__device__ __forceinline__ uint32_t slab32_off(int r, int j) { return r * 128 + ((j ^ (r & 7)) << 4); }
+
+__device__ __forceinline__ void st_slab16(uint8_t* slab, int r, const float (&v)[32]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint4 q;
+    q.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+    q.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+    q.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+    q.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+    *reinterpret_cast<uint4*>(slab + slab16_off(r, j)) = q;
+  }
+}
+__device__ __forceinline__ void ld_slab16(const uint8_t* slab, int r, float (&a)[32]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint4 q = *reinterpret_cast<const uint4*>(slab + slab16_off(r, j));
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+      a[8 * j + 2 * i] = f.x;
+      a[8 * j + 2 * i + 1] = f.y;
+    }
+  }
+}
+__device__ __forceinline__ void st_slab32(uint8_t* slab, int r, const float (&v)[32]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    *reinterpret_cast<float4*>(slab + slab32_off(r, j)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+}
+__device__ __forceinline__ void add_slab32(const uint8_t* slab, int r, float (&v)[32]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 a = *reinterpret_cast<const float4*>(slab + slab32_off(r, j));
+    v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += a.z; v[4 * j + 3] += a.w;
+  }
+}
+
+__device__ __forceinline__ void add_bias32(const float* __restrict__ bias, int col0, float (&v)[32]) {
+  const float4* b4 = reinterpret_cast<const float4*>(bias + col0);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4 b = __ldg(b4 + i);
+    v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+  }
+}
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1)
+gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                  const __grid_constant__ CUtensorMap tma_d, const __grid_constant__ CUtensorMap tma_d2,
+                  const __grid_constant__ CUtensorMap tma_aux, const Gemm2Params p) {
+  using Cfg = Cfg2<BN>;
+  constexpr int kStages = Cfg::kStages;
+  constexpr int kBHalf = Cfg::kBHalfRows;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* staging = smem + kStages * Cfg::kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + k2StagingBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* acc_full = empty_bar + kStages;     // [2]
+  uint64_t* acc_empty = acc_full + 2;           // [2]  (leader's copy is the one waited on)
+  uint64_t* aux_bar = acc_empty + 2;            // [k2EpiWarps][4]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + k2EpiWarps * 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = cluster_ctarank();
+  const bool leader = cta_rank == 0;
+  const int pair_id = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+    tma_prefetch_desc(&tma_d);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], 2 * k2EpiWarps);
+    }
+    for (int s = 0; s < k2EpiWarps * 4; ++s) mbar_init(&aux_bar[s], 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc_pair(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();          // peer barriers initialised, both TMEM allocations done
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = pair_id; w < p.total_work; w += num_pairs) {
+        const Work2 it = decode_work2(p, w);
+        const int m0 = it.m_blk * (2 * k2BM) + static_cast<int>(cta_rank) * k2BM;
+        const int n0 = it.n_blk * BN + static_cast<int>(cta_rank) * kBHalf;
+        for (int kb = it.kb_begin; kb < it.kb_end; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::kStageBytes;
+          uint8_t* sb = sa + k2ABytes;
+          const uint32_t bar = mapa_shared(smem_u32(&full_bar[stage]), 0);
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+          const int k0 = kb * k2BK;
+          if (!A_MN) {
+            tma_load_2d_pair(sa, &tma_a, bar, k0, m0);
+          } else {
+#pragma unroll
+            for (int g = 0; g < k2BM / 64; ++g) tma_load_2d_pair(sa + g * 8192, &tma_a, bar, m0 + g * 64, k0);
+          }
+          if (!B_MN) {
+            tma_load_2d_pair(sb, &tma_b, bar, k0, n0);
+          } else {
+#pragma unroll
+            for (int g = 0; g < kBHalf / 64; ++g) tma_load_2d_pair(sb + g * 8192, &tma_b, bar, n0 + g * 64, k0);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (leader) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * k2BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      constexpr uint32_t a_lbo = A_MN ? 8192u : 0u, b_lbo = B_MN ? 8192u : 0u;
+      constexpr uint32_t a_kstep = A_MN ? 2048u : 32u, b_kstep = B_MN ? 2048u : 32u;
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int w = pair_id; w < p.total_work; w += num_pairs) {
+        const Work2 it = decode_work2(p, w);
+        mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = it.kb_begin; kb < it.kb_end; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after_sync();
+          if (lane == 0) {
+            const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+            const uint32_t sb = sa + k2ABytes;
+#pragma unroll
+            for (int k = 0; k < k2BK / 16; ++k) {
+              const uint64_t ad = umma_smem_desc(sa + k * a_kstep, a_lbo, 1024);
+              const uint64_t bd = umma_smem_desc(sb + k * b_kstep, b_lbo, 1024);
+              tc_mma_bf16_pair(d_tmem, ad, bd, idesc, (kb > it.kb_begin || k > 0) ? 1u : 0u);
+            }
+            tc_commit_pair(&empty_bar[stage], 3);                         // both CTAs' producers may refill
+            if (kb == it.kb_end - 1) tc_commit_pair(&acc_full[acc], 3);   // both CTAs' epilogues may drain
+          }
+          __syncwarp();
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= k2FirstEpiWarp) {
+    // ------------------------------------------------------------------ epilogue (both CTAs)
+    const int ew = warp - k2FirstEpiWarp;
+    const int quad = warp & 3;                // TMEM lane quadrant (= warp id % 4)
+    const int col_half = ew >> 2;
+    constexpr int kChunks = BN / 64;          // 32-column chunks per warp
+    uint8_t* slabs = staging + ew * k2SlabBytes;
+    uint64_t* my_aux = aux_bar + ew * 4;
+    const int epi = p.epi;
+    const bool out_f32 = epi == VITK_EPI_BIAS_RESID_F32 || epi == VITK_EPI_ACCUM_F32 || epi == VITK_EPI_STORE_F32;
+    const bool has_aux = epi == VITK_EPI_BIAS_RESID_F32 || epi == VITK_EPI_MUL_BF16 || epi == VITK_EPI_DGELU_BF16;
+    const bool has_bias = p.bias != nullptr && (epi == VITK_EPI_BIAS_BF16 || epi == VITK_EPI_BIAS_GELU_BF16 ||
+                                                epi == VITK_EPI_BIAS_GELUG_BF16 || epi == VITK_EPI_BIAS_RESID_F32);
+    const int nslab = out_f32 ? 3 : 4;
+    const int slab_bytes = out_f32 ? 4096 : 2048;
+    const uint32_t acc_empty_leader = mapa_shared(smem_u32(&acc_empty[0]), 0);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    int slot = 0;                 // next slab (ring over nslab)
+    uint32_t aux_phase_bits = 0;  // phase of each of the 4 aux barriers
+    const uint32_t acc_empty_stride = 8;
+
+    auto tile_row0 = [&](const Work2& it) { return it.m_blk * (2 * k2BM) + static_cast<int>(cta_rank) * k2BM + quad * 32; };
+    auto tile_col0 = [&](const Work2& it) { return it.n_blk * BN + col_half * (BN / 2); };
+    auto issue_aux = [&](int s, int col, int row) {   // lane 0 only
+      mbar_arrive_expect_tx(&my_aux[s], static_cast<uint32_t>(slab_bytes));
+      tma_load_2d(slabs + s * slab_bytes, &tma_aux, &my_aux[s], col, row);
+    };
+
+    int w = pair_id;
+    if (has_aux && w < p.total_work && lane == 0) {   // prefetch the first aux slab before any accumulator is ready
+      const Work2 it = decode_work2(p, w);
+      issue_aux(slot, tile_col0(it), tile_row0(it));
+    }
+    for (; w < p.total_work; w += num_pairs) {
+      const Work2 it = decode_work2(p, w);
+      const int row0 = tile_row0(it), col0 = tile_col0(it);
+      mbar_wait(&acc_full[acc], acc_phase);
+      tc_fence_after_sync();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + col_half * (BN / 2);
+#pragma unroll 1
+      for (int c = 0; c < kChunks; ++c) {
+        const int col = col0 + c * 32;
+        uint32_t r[32];
+        tmem_ld_32x32(t_row + c * 32, r);
+        // while the TMEM load is in flight: make sure the slab we will write next is reusable and
+        // (aux modes) start fetching the NEXT chunk's aux tile into the next ring slot
+        const int cur = slot;
+        const int nxt = (slot + 1 == nslab) ? 0 : slot + 1;
+        if (has_aux) {
+          if (lane == 0) {
+            // slab `nxt` was last stored nslab-1 chunks ago: allow the newer stores to stay in flight
+            if (out_f32) tma_store_wait_read<1>(); else tma_store_wait_read<2>();
+            int ncol = col + 32, nrow = row0;
+            bool more = true;
+            if (c + 1 == kChunks) {       // first chunk of the next tile of this CTA
+              const int wn = w + num_pairs;
+              more = wn < p.total_work;
+              if (more) {
+                const Work2 nt = decode_work2(p, wn);
+                ncol = tile_col0(nt);
+                nrow = tile_row0(nt);
+              }
+            }
+            if (more) issue_aux(nxt, ncol, nrow);
+          }
+          __syncwarp();
+          mbar_wait(&my_aux[cur], (aux_phase_bits >> cur) & 1u);
+          aux_phase_bits ^= 1u << cur;
+        } else {
+          if (lane == 0) tma_store_wait_read<2>();
+          __syncwarp();
+        }
+        tmem_ld_wait();
+        if (c == kChunks - 1) {           // all TMEM reads of this tile are done: hand the buffer back early
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(acc_empty_leader + acc * acc_empty_stride);
+        }
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+        if (has_bias) add_bias32(p.bias, col, v);
+        uint8_t* slab = slabs + cur * slab_bytes;
+        bool second_store = false;
+        switch (epi) {
+          case VITK_EPI_STORE_BF16:
+          case VITK_EPI_BIAS_BF16:
+            st_slab16(slab, lane, v);
+            break;
+          case VITK_EPI_BIAS_GELU_BF16: {      // d = u, d2 = gelu(u)
+            st_slab16(slab, lane, v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+            st_slab16(slabs + nxt * slab_bytes, lane, v);
+            second_store = true;
+            break;
+          }
+          case VITK_EPI_BIAS_GELUG_BF16: {     // d = gelu(u), d2 = gelu'(u) (optional)
+            float gr[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const GeluParts g = gelu_parts(v[i]);
+              gr[i] = fmaf(v[i], g.pdf, g.cdf);
+              v[i] *= g.cdf;
+            }
+            st_slab16(slab, lane, v);
+            if (p.has_d2) {
+              st_slab16(slabs + nxt * slab_bytes, lane, gr);
+              second_store = true;
+            }
+            break;
+          }
+          case VITK_EPI_MUL_BF16:
+          case VITK_EPI_DGELU_BF16: {
+            float a[32];
+            ld_slab16(slab, lane, a);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] *= (epi == VITK_EPI_MUL_BF16) ? a[i] : gelu_erf_grad(a[i]);
+            st_slab16(slab, lane, v);
+            break;
+          }
+          case VITK_EPI_BIAS_RESID_F32:
+            add_slab32(slab, lane, v);
+            st_slab32(slab, lane, v);
+            break;
+          default:  // VITK_EPI_ACCUM_F32, VITK_EPI_STORE_F32
+            st_slab32(slab, lane, v);
+            break;
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (epi == VITK_EPI_ACCUM_F32) tma_reduce_add_2d(&tma_d, slab, col, row0);
+          else tma_store_2d(&tma_d, slab, col, row0);
+          tma_store_commit();
+          if (second_store) {
+            tma_store_2d(&tma_d2, slabs + nxt * slab_bytes, col, row0);
+            tma_store_commit();
+          }
+        }
+        slot = nxt;
+        if (second_store) slot = (slot + 1 == nslab) ? 0 : slot + 1;
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+    if (lane == 0) tma_store_wait_all<0>();   // smem must outlive the bulk reads; writes complete before exit
+  }
+  __syncwarp();
+
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();   // neither CTA may free TMEM / exit while the peer can still reach it
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------- host side
+static int out_map(CUtensorMap* m, const void* base, bool f32, long long rows, long long cols, long long ld) {
+  const uint64_t dims[2] = {static_cast<uint64_t>(cols), static_cast<uint64_t>(rows)};
+  const uint64_t str[1] = {static_cast<uint64_t>(ld) * (f32 ? 4 : 2)};
+  const uint32_t box[2] = {32, 32};
+  return get_tensor_map(m, base, f32 ? TM_F32 : TM_BF16, 2, dims, str, box, f32 ? TM_SW128 : TM_SW64);
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch_gemm2(const vitk_gemm_args& a, const Gemm2Params& p, int pairs, cudaStream_t stream) {
+  using Cfg = Cfg2<BN>;
+  CUtensorMap ta, tb, td, td2, taux;
+  {
+    uint64_t dims[2], str[1];
+    uint32_t box[2];
+    if (!A_MN) { dims[0] = a.K; dims[1] = a.M; box[0] = k2BK; box[1] = k2BM; }
+    else       { dims[0] = a.M; dims[1] = a.K; box[0] = 64;   box[1] = k2BK; }
+    str[0] = static_cast<uint64_t>(a.lda) * 2;
+    if (int rc = make_tensor_map_bf16(&ta, a.a, 2, dims, str, box)) return rc;
+    if (!B_MN) { dims[0] = a.K; dims[1] = a.N; box[0] = k2BK; box[1] = Cfg::kBHalfRows; }
+    else       { dims[0] = a.N; dims[1] = a.K; box[0] = 64;   box[1] = k2BK; }
+    str[0] = static_cast<uint64_t>(a.ldb) * 2;
+    if (int rc = make_tensor_map_bf16(&tb, a.b, 2, dims, str, box)) return rc;
+  }
+  const bool f32_out = a.epilogue == VITK_EPI_BIAS_RESID_F32 || a.epilogue == VITK_EPI_ACCUM_F32 || a.epilogue == VITK_EPI_STORE_F32;
+  if (int rc = out_map(&td, a.d, f32_out, a.M, a.N, a.ldd)) return rc;
+  td2 = td;
+  taux = td;
+  if (a.d2 != nullptr) { if (int rc = out_map(&td2, a.d2, false, a.M, a.N, a.ldd)) return rc; }
+  if (a.aux != nullptr) { if (int rc = out_map(&taux, a.aux, a.epilogue == VITK_EPI_BIAS_RESID_F32, a.M, a.N, a.ld_aux)) return rc; }
+  auto kern = gemm2_bf16_kernel<BN, A_MN, B_MN>;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [&] {
+    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+  });
+  if (attr_err != cudaSuccess) return cuda_error(attr_err, "cudaFuncSetAttribute(gemm2 smem)");
+  kern<<<2 * pairs, k2Threads, Cfg::kSmemBytes, stream>>>(ta, tb, td, td2, taux, p);
+  VITK_LAUNCH_CHECK("gemm2_bf16_kernel");
+  return 0;
+}
+
+template <int BN>
+static int dispatch_major2(const vitk_gemm_args& a, const Gemm2Params& p, int pairs, cudaStream_t s) {
+  if (!a.a_mn_major && !a.b_mn_major) return launch_gemm2<BN, false, false>(a, p, pairs, s);
+  if (a.a_mn_major && !a.b_mn_major) return launch_gemm2<BN, true, false>(a, p, pairs, s);
+  if constexpr (BN != 192) {     // an MN-major B half must be whole 64-column TMA boxes
+    if (!a.a_mn_major && a.b_mn_major) return launch_gemm2<BN, false, true>(a, p, pairs, s);
+    return launch_gemm2<BN, true, true>(a, p, pairs, s);
+  }
+  return set_error(VITK_EINVAL, "gemm2: tile_n 192 needs a K-major B operand");
+}
+
+// cost ∝ waves × per-tile MMA time (∝ BN), with a small penalty for the lower arithmetic intensity of
+// narrow tiles; split-K (wgrad only) multiplies the work items until one wave is full.
+static void choose_tiling2(const vitk_gemm_args& a, int pairs, int* bn_out, int* splits_out) {
+  const long long mt = (a.M + 2 * k2BM - 1) / (2 * k2BM);
+  const long long kb_total = (a.K + k2BK - 1) / k2BK;
+  double best = 1e30;
+  const int cands[3] = {256, 192, 128};
+  for (int bn : cands) {
+    if (a.N % bn) continue;
+    if (a.b_mn_major && bn == 192) continue;
+    if (a.tile_n && a.tile_n != bn) continue;
+    const long long tiles = mt * (a.N / bn);
+    int splits = 1;
+    if (a.epilogue == VITK_EPI_ACCUM_F32) {
+      if (a.split_k > 0) splits = a.split_k;
+      else if (tiles < pairs) {
+        splits = static_cast<int>(pairs / tiles);
+        const long long cap = kb_total / 4 > 0 ? kb_total / 4 : 1;
+        if (splits > cap) splits = static_cast<int>(cap);
+        if (splits < 1) splits = 1;
+      }
+    }
+    const long long kb_per = (kb_total + splits - 1) / splits;
+    const long long items = tiles * ((kb_total + kb_per - 1) / kb_per);
+    const long long waves = (items + pairs - 1) / pairs;
+    const double penalty = bn == 128 ? 1.12 : (bn == 192 ? 1.04 : 1.0);
+    const double cost = static_cast<double>(waves) * (kb_per * bn + 2.0 * bn /*epilogue / fill*/) * penalty;
+    if (cost < best - 1e-9) { best = cost; *bn_out = bn; *splits_out = splits; }
+  }
+}
+
+// Called by vitk_gemm_bf16 (gemm.cu) after argument validation.  Returns VITK_EINVAL-free 1 when the
+// problem is not eligible for the pair kernel so that the caller falls through to the 1-CTA kernel.
+int gemm2_try_launch(const vitk_gemm_args& a, cudaStream_t stream, bool* handled) {
+  *handled = false;
+  if (a.variant == 1) return 0;
+  const bool eligible = a.epilogue != VITK_EPI_PATCH_F32 && a.N % 128 == 0 && a.max_ctas == 0 &&
+                        (a.tile_n == 0 || a.tile_n == 128 || a.tile_n == 192 || a.tile_n == 256) &&
+                        !(a.tile_n == 192 && a.b_mn_major);
+  if (!eligible) {
+    VITK_REQUIRE(a.variant != 2, VITK_EINVAL, "gemm: the CTA-pair kernel does not support this problem (epilogue %d, tile_n %d)",
+                 a.epilogue, a.tile_n);
+    return 0;
+  }
+  const int sms = num_sms();
+  const int pairs_avail = sms / 2;
+  int bn = 0, splits = 1;
+  choose_tiling2(a, pairs_avail, &bn, &splits);
+  if (bn == 0) {
+    VITK_REQUIRE(a.variant != 2, VITK_EINVAL, "gemm: no CTA-pair tiling for N=%lld tile_n=%d", (long long)a.N, a.tile_n);
+    return 0;
+  }
+  Gemm2Params p;
+  p.M = static_cast<int>(a.M); p.N = static_cast<int>(a.N); p.K = static_cast<int>(a.K);
+  const int m_tiles = (p.M + 2 * k2BM - 1) / (2 * k2BM);
+  p.n_tiles = p.N / bn;
+  p.mn_tiles = m_tiles * p.n_tiles;
+  p.kb_total = (p.K + k2BK - 1) / k2BK;
+  if (splits > p.kb_total) splits = p.kb_total;
+  p.kb_per_split = (p.kb_total + splits - 1) / splits;
+  p.k_splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+  p.total_work = p.mn_tiles * p.k_splits;
+  p.epi = a.epilogue;
+  p.has_d2 = a.d2 != nullptr;
+  p.bias = a.bias;
+  const int pairs = p.total_work < pairs_avail ? p.total_work : pairs_avail;
+  *handled = true;
+  switch (bn) {
+    case 256: return dispatch_major2<256>(a, p, pairs, stream);
+    case 192: return dispatch_major2<192>(a, p, pairs, stream);
+    default: return dispatch_major2<128>(a, p, pairs, stream);
+  }
+}
+
+}  // namespace vitk

@@ -22,7 +22,7 @@ from typing import Callable, Dict, List, Optional, Tuple
 import torch
 
 from . import _lib, ops
-from ._lib import (EPI_ACCUM_F32, EPI_BIAS_BF16, EPI_BIAS_GELU_BF16, EPI_BIAS_RESID_F32, EPI_DGELU_BF16, EPI_PATCH_F32,
+from ._lib import (EPI_ACCUM_F32, EPI_BIAS_BF16, EPI_BIAS_GELUG_BF16, EPI_BIAS_RESID_F32, EPI_MUL_BF16, EPI_PATCH_F32,
                    EPI_STORE_BF16, GemmArgs)
 
 bf16, f32 = torch.bfloat16, torch.float32
@@ -40,7 +40,7 @@ class _Plan:
         self.steps.append((getattr(_lib.lib(), name), args, name))
 
     def gemm(self, a, b, M, N, K, d, epilogue, a_mn=False, b_mn=False, d2=None, bias=None, aux=None, rows_in=0,
-             rows_out=0, row_off=0, ldd=None, ld_aux=None, split_k=0, tile_n=0):
+             rows_out=0, row_off=0, ldd=None, ld_aux=None, split_k=0, tile_n=0, variant=0):
         g = GemmArgs()
         g.a, g.b, g.M, g.N, g.K = a.data_ptr(), b.data_ptr(), M, N, K
         g.lda, g.ldb = a.stride(0), b.stride(0)
@@ -50,7 +50,7 @@ class _Plan:
         g.bias = None if bias is None else bias.data_ptr()
         g.aux = None if aux is None else aux.data_ptr()
         g.ld_aux = (ld_aux if ld_aux is not None else (aux.stride(0) if aux is not None else 0))
-        g.rows_in, g.rows_out, g.row_off, g.tile_n, g.max_ctas = rows_in, rows_out, row_off, tile_n, 0
+        g.rows_in, g.rows_out, g.row_off, g.tile_n, g.max_ctas, g.variant = rows_in, rows_out, row_off, tile_n, 0, variant
         self._keep.append(g)
         self.gemm_flops[len(self.steps)] = 2.0 * M * N * K
         self.steps.append((_lib.lib().vitk_gemm_bf16, (C.byref(g),), "vitk_gemm_bf16"))
@@ -97,7 +97,7 @@ class Arena:
         self.qkv = [new((M, 3 * D), bf16) for _ in range(nl)]
         self.o = [new((M, D), bf16) for _ in range(nl)]
         self.lse = [new((B, H, T), f32) for _ in range(nl)]
-        self.u = [new((M, Fi), bf16) for _ in range(nl)]
+        self.gp = [new((M, Fi), bf16) for _ in range(nl)] if train else None     # gelu'(u), saved for backward
         self.a = [new((M, Fi), bf16) for _ in range(nl)]
         self.labels = new((B, Cn), f32)
         self.logits = new((B, Cn), f32)
@@ -143,7 +143,8 @@ class Arena:
             pl.add("vitk_attn_fwd", _p(self.qkv[i]), B, T, H, scale, _p(self.o[i]), _p(self.lse[i]))
             pl.gemm(self.o[i], lw["wo16"], M, D, D, h1, EPI_BIAS_RESID_F32, bias=lw["bo"], aux=hin)
             pl.add("vitk_layernorm_fwd", _p(h1), D, _p(lw["g2"]), _p(lw["b2"]), eps, M, D, _p(self.n2[i]), _p(st[2]), _p(st[3]))
-            pl.gemm(self.n2[i], lw["w1_16"], M, Fi, D, self.u[i], EPI_BIAS_GELU_BF16, d2=self.a[i], bias=lw["bf1"])
+            pl.gemm(self.n2[i], lw["w1_16"], M, Fi, D, self.a[i], EPI_BIAS_GELUG_BF16, d2=self.gp[i] if self.train else None,
+                    bias=lw["bf1"])
             pl.gemm(self.a[i], lw["w2_16"], M, D, Fi, hout, EPI_BIAS_RESID_F32, bias=lw["bf2"], aux=h1)
         hl = self.h[L] if self.train else self.h[0]
         self.h_last = hl
@@ -172,7 +173,7 @@ class Arena:
             # MLP
             pl.gemm(dh, self.a[l], D, Fi, M, lg["w2"], EPI_ACCUM_F32, a_mn=True, b_mn=True)
             pl.add("vitk_colsum_bf16", _p(dh), M, D, D, _p(lg["bf2"]))
-            pl.gemm(dh, lw["w2_16"], M, Fi, D, self.du, EPI_DGELU_BF16, b_mn=True, aux=self.u[l])
+            pl.gemm(dh, lw["w2_16"], M, Fi, D, self.du, EPI_MUL_BF16, b_mn=True, aux=self.gp[l])
             pl.gemm(self.du, self.n2[l], Fi, D, M, lg["w1"], EPI_ACCUM_F32, a_mn=True, b_mn=True)
             pl.add("vitk_colsum_bf16", _p(self.du), M, Fi, Fi, _p(lg["bf1"]))
             pl.gemm(self.du, lw["w1_16"], M, D, Fi, self.dn, EPI_STORE_BF16, b_mn=True)

@@ -13,8 +13,8 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import (EPI_ACCUM_F32, EPI_BIAS_BF16, EPI_BIAS_GELU_BF16, EPI_BIAS_RESID_F32, EPI_DGELU_BF16,  # noqa: F401
-                   EPI_PATCH_F32, EPI_STORE_BF16, EPI_STORE_F32, GemmArgs)
+from ._lib import (EPI_ACCUM_F32, EPI_BIAS_BF16, EPI_BIAS_GELU_BF16, EPI_BIAS_GELUG_BF16, EPI_BIAS_RESID_F32,  # noqa: F401
+                   EPI_DGELU_BF16, EPI_MUL_BF16, EPI_PATCH_F32, EPI_STORE_BF16, EPI_STORE_F32, GemmArgs)
 
 bf16, f32 = torch.bfloat16, torch.float32
 
@@ -91,7 +91,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int, d: torch.Tens
          a_mn_major: bool = False, b_mn_major: bool = False, lda: Optional[int] = None, ldb: Optional[int] = None,
          ldd: Optional[int] = None, d2: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
          aux: Optional[torch.Tensor] = None, ld_aux: int = 0, rows_in: int = 0, rows_out: int = 0, row_off: int = 0,
-         split_k: int = 0, tile_n: int = 0, max_ctas: int = 0) -> torch.Tensor:
+         split_k: int = 0, tile_n: int = 0, max_ctas: int = 0, variant: int = 0) -> torch.Tensor:
     """D[M,N] = A·Bᵀ (logical A [M,K], B [N,K]) on tcgen05 with a fused epilogue; see vitk.h."""
     g = GemmArgs()
     g.a, g.b = a.data_ptr(), b.data_ptr()
@@ -106,7 +106,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int, d: torch.Tens
     g.aux = _ptr(aux)
     g.ld_aux = ld_aux if ld_aux else (aux.stride(0) if aux is not None else 0)
     g.rows_in, g.rows_out, g.row_off = rows_in, rows_out, row_off
-    g.tile_n, g.max_ctas = tile_n, max_ctas
+    g.tile_n, g.max_ctas, g.variant = tile_n, max_ctas, variant
     _lib.check(_lib.lib().vitk_gemm_bf16(C.byref(g), _stream()), "gemm_bf16")
     return d
 

@@ -74,7 +74,10 @@ VITK_API int vitk_layernorm_bwd(const void* dy_bf16, const float* x, int64_t ldx
  *   a_mn_major = 0: A stored [M,K] with K contiguous, lda = row stride (elements)
  *   a_mn_major = 1: A stored [K,M] with M contiguous, lda = stride between k-rows
  *   (same for B with N).  lda/ldb multiples of 8, base pointers 16-byte aligned.
- * N must be a multiple of 128. */
+ * N must be a multiple of 128.  Two kernels sit behind this entry point: a CTA-pair kernel
+ * (tcgen05 cta_group::2, 256×{128,192,256} tiles, epilogue through swizzled shared memory and TMA
+ * stores / TMA reduce-add) used whenever it applies, and a single-CTA kernel (128×N tiles) that
+ * also handles the row-remapping patch-embedding epilogue. */
 enum vitk_epilogue {
   VITK_EPI_STORE_BF16 = 0,      /* d bf16 = acc                                  (dgrad)   */
   VITK_EPI_BIAS_BF16 = 1,       /* d bf16 = acc + bias[n]                        (QKV)     */
@@ -84,7 +87,9 @@ enum vitk_epilogue {
                                    acc + bias[n] + aux_f32[row_off + m%rows_in, n] (patch+pos) */
   VITK_EPI_DGELU_BF16 = 5,      /* d bf16 = acc * gelu'(aux_bf16[m,n])           (fc2 dgrad)*/
   VITK_EPI_ACCUM_F32 = 6,       /* d f32 += acc (red.global.add; split-K allowed) (wgrad)  */
-  VITK_EPI_STORE_F32 = 7        /* d f32 = acc                                             */
+  VITK_EPI_STORE_F32 = 7,       /* d f32 = acc                                             */
+  VITK_EPI_BIAS_GELUG_BF16 = 8, /* u = acc + bias; d bf16 = gelu_erf(u); d2 bf16 (optional) = gelu_erf'(u)  (fc1, training) */
+  VITK_EPI_MUL_BF16 = 9         /* d bf16 = acc * aux_bf16[m,n]                  (fc2 dgrad with saved gelu') */
 };
 
 typedef struct vitk_gemm_args {
@@ -103,7 +108,9 @@ typedef struct vitk_gemm_args {
   int64_t ld_aux;
   int64_t rows_in, rows_out, row_off; /* VITK_EPI_PATCH_F32 row remap */
   int32_t tile_n;        /* 0 = library chooses; else 128, 192 or 256 */
-  int32_t max_ctas;      /* 0 = all SMs; else cap on the persistent grid */
+  int32_t max_ctas;      /* 0 = all SMs; else cap on the persistent grid (single-CTA kernel only) */
+  int32_t variant;       /* 0 = library chooses; 1 = single-CTA 128×N tiles (gemm.cu); 2 = CTA pair,
+                            256×N tiles, TMA-store epilogue (gemm2.cu; not for VITK_EPI_PATCH_F32) */
 } vitk_gemm_args;
 
 VITK_API int vitk_gemm_bf16(const vitk_gemm_args* args, vitk_stream_t stream);

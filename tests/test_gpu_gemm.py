@@ -37,50 +37,72 @@ SHAPES = [
 ]
 
 
+@pytest.mark.parametrize("variant", [1, 2])
 @pytest.mark.parametrize("M,N,K", SHAPES)
 @pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True), (True, False)])
-def test_store_f32_all_layouts(ops, M, N, K, a_mn, b_mn):
+def test_store_f32_all_layouts(ops, M, N, K, a_mn, b_mn, variant):
     if a_mn and M % 8:
         pytest.skip("MN-major A needs lda multiple of 8")
     if (not a_mn or not b_mn) and K % 8:
         pytest.skip("K-major operand needs K multiple of 8")
     a, b, ref = _operands(M, N, K, a_mn, b_mn, M + N + K)
     d = torch.full((M, N), float("nan"), device=dev)
-    ops.gemm(a, b, M, N, K, d, epilogue=ops.EPI_STORE_F32, a_mn_major=a_mn, b_mn_major=b_mn)
+    ops.gemm(a, b, M, N, K, d, epilogue=ops.EPI_STORE_F32, a_mn_major=a_mn, b_mn_major=b_mn, variant=variant)
     torch.cuda.synchronize()
     err = (d - ref).abs().max().item()
     assert err <= _tol(K, ref), f"max err {err}"
 
 
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("b_mn", [False, True])
 @pytest.mark.parametrize("tile_n", [128, 192, 256])
-@pytest.mark.parametrize("M,N,K", [(1154, 768, 768), (300, 2304, 192), (9232, 3072, 768)])
-def test_tile_shapes(ops, M, N, K, tile_n):
+@pytest.mark.parametrize("M,N,K", [(1154, 768, 768), (300, 2304, 192), (9232, 3072, 768), (16, 768, 64)])
+def test_tile_shapes(ops, M, N, K, tile_n, b_mn, variant):
     if N % tile_n:
         pytest.skip("N not a multiple of the tile")
-    a, b, ref = _operands(M, N, K, False, False, 5)
+    if variant == 2 and tile_n == 192 and b_mn:
+        pytest.skip("the CTA-pair kernel needs whole 64-column boxes for an MN-major B half")
+    a, b, ref = _operands(M, N, K, False, b_mn, 5)
     d = torch.full((M, N), float("nan"), device=dev, dtype=bf16)
-    ops.gemm(a, b, M, N, K, d, epilogue=ops.EPI_STORE_BF16, tile_n=tile_n)
+    ops.gemm(a, b, M, N, K, d, epilogue=ops.EPI_STORE_BF16, tile_n=tile_n, b_mn_major=b_mn, variant=variant)
     err = (d.float() - ref).abs().max().item()
     assert err <= _tol(K, ref) + 2 ** -8 * ref.abs().max().item(), f"max err {err}"
 
 
-def test_bias_and_gelu_epilogues(ops):
+@pytest.mark.parametrize("variant", [1, 2])
+def test_bias_and_gelu_epilogues(ops, variant):
     M, N, K = 1154, 3072, 768
     a, b, ref = _operands(M, N, K, False, False, 11)
     bias = torch.randn(N, device=dev) * 0.5
     u = torch.empty((M, N), device=dev, dtype=bf16)
     act = torch.empty((M, N), device=dev, dtype=bf16)
-    ops.gemm(a, b, M, N, K, u, epilogue=ops.EPI_BIAS_GELU_BF16, d2=act, bias=bias)
+    ops.gemm(a, b, M, N, K, u, epilogue=ops.EPI_BIAS_GELU_BF16, d2=act, bias=bias, variant=variant)
     ur = ref + bias
     assert (u.float() - ur).abs().max() <= _tol(K, ur) + 2 ** -8 * ur.abs().max()
     gr = torch.nn.functional.gelu(ur)
     assert (act.float() - gr).abs().max() <= _tol(K, ur) + 2 ** -8 * gr.abs().max()
     d = torch.empty((M, N), device=dev, dtype=bf16)
-    ops.gemm(a, b, M, N, K, d, epilogue=ops.EPI_BIAS_BF16, bias=bias)
+    ops.gemm(a, b, M, N, K, d, epilogue=ops.EPI_BIAS_BF16, bias=bias, variant=variant)
     assert torch.equal(d, u)
+    # training form: gelu(u) and gelu'(u), then the backward multiplier epilogue
+    act2 = torch.empty((M, N), device=dev, dtype=bf16)
+    gp = torch.empty((M, N), device=dev, dtype=bf16)
+    ops.gemm(a, b, M, N, K, act2, epilogue=ops.EPI_BIAS_GELUG_BF16, d2=gp, bias=bias, variant=variant)
+    assert (act2.float() - gr).abs().max() <= _tol(K, ur) + 2 ** -8 * gr.abs().max()
+    uf = ur.clone().requires_grad_(True)
+    torch.nn.functional.gelu(uf).sum().backward()
+    assert (gp.float() - uf.grad).abs().max() <= _tol(K, ur) + 2 ** -8 * 1.2
+    act3 = torch.full((M, N), float("nan"), device=dev, dtype=bf16)
+    ops.gemm(a, b, M, N, K, act3, epilogue=ops.EPI_BIAS_GELUG_BF16, bias=bias, variant=variant)     # inference: no d2
+    assert torch.equal(act3, act2)
+    mul = torch.empty((M, N), device=dev, dtype=bf16)
+    ops.gemm(a, b, M, N, K, mul, epilogue=ops.EPI_MUL_BF16, aux=gp, variant=variant)
+    rm = ref * gp.float()
+    assert (mul.float() - rm).abs().max() <= _tol(K, rm) + 2 ** -8 * rm.abs().max()
 
 
-def test_gelu_matches_erf_form_pointwise(ops):
+@pytest.mark.parametrize("variant", [1, 2])
+def test_gelu_matches_erf_form_pointwise(ops, variant):
     """K=8 identity-like GEMM isolates the epilogue: gelu in the epilogue vs torch erf GELU."""
     M, N, K = 256, 128, 64
     x = torch.linspace(-8, 8, M * N, device=dev).view(M, N)
@@ -93,24 +115,25 @@ def test_gelu_matches_erf_form_pointwise(ops):
     dgrad = torch.empty((M, N), device=dev, dtype=bf16)
     a[:, 0] = 1.0
     b[:, 0] = 1.0   # acc = 1 everywhere
-    ops.gemm(a, b, M, N, K, dgrad, epilogue=ops.EPI_DGELU_BF16, aux=pre)
+    ops.gemm(a, b, M, N, K, dgrad, epilogue=ops.EPI_DGELU_BF16, aux=pre, variant=variant)
     xf = pre.float().requires_grad_(True)
     torch.nn.functional.gelu(xf).sum().backward()
     assert (dgrad.float() - xf.grad).abs().max() <= 2 ** -8 * 1.2 + 1e-6
 
 
-def test_bias_resid_and_patch_epilogues(ops):
+@pytest.mark.parametrize("variant", [1, 2])
+def test_bias_resid_and_patch_epilogues(ops, variant):
     M, N, K = 1154, 768, 768
     a, b, ref = _operands(M, N, K, False, False, 13)
     bias = torch.randn(N, device=dev)
     res = torch.randn(M, N, device=dev)
     d = torch.empty((M, N), device=dev)
-    ops.gemm(a, b, M, N, K, d, epilogue=ops.EPI_BIAS_RESID_F32, bias=bias, aux=res)
+    ops.gemm(a, b, M, N, K, d, epilogue=ops.EPI_BIAS_RESID_F32, bias=bias, aux=res, variant=variant)
     rr = ref + bias + res
     assert (d - rr).abs().max() <= _tol(K, rr)
     # in-place residual (d == aux) is how the engine updates the residual stream
     d2 = res.clone()
-    ops.gemm(a, b, M, N, K, d2, epilogue=ops.EPI_BIAS_RESID_F32, bias=bias, aux=d2)
+    ops.gemm(a, b, M, N, K, d2, epilogue=ops.EPI_BIAS_RESID_F32, bias=bias, aux=d2, variant=variant)
     assert (d2 - rr).abs().max() <= _tol(K, rr)
     # patch embedding row remap: B images × P patches → rows 1+p of a [B, P+1, N] buffer
     Bn, P = 2, 576
@@ -125,8 +148,9 @@ def test_bias_resid_and_patch_epilogues(ops):
     assert (out[:, 0] == 7.0).all()
 
 
+@pytest.mark.parametrize("variant", [1, 2])
 @pytest.mark.parametrize("split_k", [0, 1, 3, 8])
-def test_wgrad_accumulate_split_k(ops, split_k):
+def test_wgrad_accumulate_split_k(ops, split_k, variant):
     """wgrad shape: small M×N, long ragged K, both operands MN-major, accumulate into fp32."""
     M, N, K = 768, 768, 9232
     g = torch.Generator().manual_seed(21)
@@ -134,7 +158,7 @@ def test_wgrad_accumulate_split_k(ops, split_k):
     x = torch.randn(K, N, generator=g).to(dev).to(bf16)             # [tokens, in]   → B stored [K, N]
     ref = dy.float().t() @ x.float()
     d = torch.ones((M, N), device=dev)
-    ops.gemm(dy, x, M, N, K, d, epilogue=ops.EPI_ACCUM_F32, a_mn_major=True, b_mn_major=True, split_k=split_k)
+    ops.gemm(dy, x, M, N, K, d, epilogue=ops.EPI_ACCUM_F32, a_mn_major=True, b_mn_major=True, split_k=split_k, variant=variant)
     err = (d - 1 - ref).abs().max().item()
     assert err <= _tol(K, ref) * 4, f"max err {err}"
 
