@@ -10,14 +10,16 @@
 //                 both CTAs' loads complete on the LEADER's full barrier
 //   warp 1        TMEM allocation (both CTAs); in the leader, lane 0 issues the MMAs and commits to
 //                 the stage-empty barriers (multicast to both CTAs) and the accumulator-full barriers
-//   warps 2,3     idle (keep warp id % 4 of the epilogue warps aligned with their TMEM lane quadrant)
-//   warps 4..11   epilogue: TMEM → registers → fused math → 32×32 slab in swizzled smem → TMA store
-//                 (or TMA reduce-add for split-K wgrad); residual / multiplier tiles arrive by TMA
-//                 load into the same slab and are updated in place.  No per-thread global access:
-//                 every byte of C/D traffic is a full-line TMA transaction, M tails are clipped by TMA.
+//   (epilogue warp w may only touch TMEM lanes 32·(w%4)…: quadrant = warp id % 4)
+//   warps 2..9    epilogue: TMEM → registers (one row per thread) → fused math → [32 rows × 64 B] slab in
+//                 swizzled smem → TMA store (TMA reduce-add for split-K wgrad).  Shared-memory bandwidth
+//                 is the scarce resource (the operand pipeline alone moves 64 B/clk in and 64 B/clk out
+//                 at full MMA rate), so outputs cross smem exactly twice; residual / multiplier tiles
+//                 are read two chunks ahead with coalesced loads and transposed through a third slab.
 //   accumulators  double-buffered in TMEM (2×BN columns) so the epilogue of tile i overlaps the MMAs
 //                 of tile i+1.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include <mutex>
 
@@ -31,11 +33,12 @@ namespace vitk {
 constexpr int k2BM = 128;            // rows per CTA (256 per pair)
 constexpr int k2BK = 64;
 constexpr int k2EpiWarps = 8;
-constexpr int k2FirstEpiWarp = 4;
+constexpr int k2FirstEpiWarp = 2;
 constexpr int k2Threads = (k2FirstEpiWarp + k2EpiWarps) * 32;   // 384
 constexpr int k2ABytes = k2BM * k2BK * 2;                       // 16 KB
-constexpr int k2SlabBytes = 12288;                              // per epilogue warp: 3×4 KB (f32) or 4×2 KB (bf16)
-constexpr int k2StagingBytes = k2EpiWarps * k2SlabBytes;        // 96 KB
+constexpr int k2SlabBytes = 6144;                               // per epilogue warp: 3 slabs of [32 rows × 64 B]
+constexpr int k2StagingBytes = k2EpiWarps * k2SlabBytes;        // 48 KB
+constexpr int k2BiasBytes = k2EpiWarps * 128 * 4;                // per-warp bias slice (≤128 floats)
 constexpr int k2BarBytes = 1024;
 
 template <int BN>
@@ -43,9 +46,9 @@ struct Cfg2 {
   static constexpr int kBHalfRows = BN / 2;
   static constexpr int kBBytes = kBHalfRows * k2BK * 2;
   static constexpr int kStageBytes = k2ABytes + kBBytes;
-  static constexpr int kStages = (BN == 128) ? 5 : 4;
+  static constexpr int kStages = (BN == 256) ? 5 : (BN == 192 ? 6 : 7);   // 160 / 168 / 168 KB of operands in flight
   static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;
-  static constexpr int kSmemBytes = kStages * kStageBytes + k2StagingBytes + k2BarBytes + 1024 /*align slack*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + k2StagingBytes + k2BiasBytes + k2BarBytes + 1024 /*align slack*/;
 };
 
 struct Gemm2Params {
@@ -53,6 +56,9 @@ struct Gemm2Params {
   int n_tiles, mn_tiles, k_splits, kb_per_split, kb_total, total_work;
   int epi;
   int has_d2;
+  int dbg;            // VITK_GEMM_DBG experiment bits (0 in production): 1 skip stores, 2 skip aux, 4 skip TMEM loads
+  const void* aux;
+  long long ld_aux;
   const float* bias;
 };
 
@@ -126,19 +132,18 @@ template <int BN, bool A_MN, bool B_MN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                   const __grid_constant__ CUtensorMap tma_d, const __grid_constant__ CUtensorMap tma_d2,
-                  const __grid_constant__ CUtensorMap tma_aux, const Gemm2Params p) {
+                  const Gemm2Params p) {
   using Cfg = Cfg2<BN>;
   constexpr int kStages = Cfg::kStages;
   constexpr int kBHalf = Cfg::kBHalfRows;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* staging = smem + kStages * Cfg::kStageBytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + k2StagingBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + k2StagingBytes + k2BiasBytes);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* acc_full = empty_bar + kStages;     // [2]
   uint64_t* acc_empty = acc_full + 2;           // [2]  (leader's copy is the one waited on)
-  uint64_t* aux_bar = acc_empty + 2;            // [k2EpiWarps][4]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + k2EpiWarps * 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -150,7 +155,6 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
-    tma_prefetch_desc(&tma_d);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -159,7 +163,6 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       mbar_init(&acc_full[s], 1);
       mbar_init(&acc_empty[s], 2 * k2EpiWarps);
     }
-    for (int s = 0; s < k2EpiWarps * 4; ++s) mbar_init(&aux_bar[s], 1);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc_pair(tmem_slot, Cfg::kTmemCols);
@@ -240,147 +243,218 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     }
   } else if (warp >= k2FirstEpiWarp) {
     // ------------------------------------------------------------------ epilogue (both CTAs)
+    // Thread = one accumulator row (TMEM lane).  A chunk is 64 bytes of output per row (32 bf16 or
+    // 16 fp32 columns): registers → [32 rows × 64 B] slab in 64-byte-swizzled smem → one TMA store
+    // (TMA reduce-add for split-K wgrad), two chunks in flight per warp.  Residual / multiplier tiles
+    // are read two chunks ahead with coalesced 128-bit loads (registers) and transposed through a
+    // third slab, so the SM's TMA queue carries only operand loads and output stores.
     const int ew = warp - k2FirstEpiWarp;
     const int quad = warp & 3;                // TMEM lane quadrant (= warp id % 4)
     const int col_half = ew >> 2;
-    constexpr int kChunks = BN / 64;          // 32-column chunks per warp
-    uint8_t* slabs = staging + ew * k2SlabBytes;
-    uint64_t* my_aux = aux_bar + ew * 4;
+    uint8_t* slabs = staging + ew * k2SlabBytes;            // 3 × 2 KB
+    float* bias_s = reinterpret_cast<float*>(staging + k2StagingBytes) + ew * 128;   // this warp's bias slice
     const int epi = p.epi;
     const bool out_f32 = epi == VITK_EPI_BIAS_RESID_F32 || epi == VITK_EPI_ACCUM_F32 || epi == VITK_EPI_STORE_F32;
-    const bool has_aux = epi == VITK_EPI_BIAS_RESID_F32 || epi == VITK_EPI_MUL_BF16 || epi == VITK_EPI_DGELU_BF16;
+    const bool has_aux = !(p.dbg & 2) && (epi == VITK_EPI_BIAS_RESID_F32 || epi == VITK_EPI_MUL_BF16 || epi == VITK_EPI_DGELU_BF16);
     const bool has_bias = p.bias != nullptr && (epi == VITK_EPI_BIAS_BF16 || epi == VITK_EPI_BIAS_GELU_BF16 ||
                                                 epi == VITK_EPI_BIAS_GELUG_BF16 || epi == VITK_EPI_BIAS_RESID_F32);
-    const int nslab = out_f32 ? 3 : 4;
-    const int slab_bytes = out_f32 ? 4096 : 2048;
+    const int cw = out_f32 ? 16 : 32;                      // chunk width in columns
+    const int nchunks = (BN / 2) / cw;
+    const int nout = has_aux ? 2 : 3;                      // output slabs in the ring (slab 2 transposes aux)
+    const int aux_esize = out_f32 ? 4 : 2;
     const uint32_t acc_empty_leader = mapa_shared(smem_u32(&acc_empty[0]), 0);
     int acc = 0;
     uint32_t acc_phase = 0;
-    int slot = 0;                 // next slab (ring over nslab)
-    uint32_t aux_phase_bits = 0;  // phase of each of the 4 aux barriers
-    const uint32_t acc_empty_stride = 8;
+    int oslot = 0;
+    const int rc = lane >> 2, jc = lane & 3;               // coalesced layout: iteration i ↔ row 8i + rc, 16-byte chunk jc
 
     auto tile_row0 = [&](const Work2& it) { return it.m_blk * (2 * k2BM) + static_cast<int>(cta_rank) * k2BM + quad * 32; };
     auto tile_col0 = [&](const Work2& it) { return it.n_blk * BN + col_half * (BN / 2); };
-    auto issue_aux = [&](int s, int col, int row) {   // lane 0 only
-      mbar_arrive_expect_tx(&my_aux[s], static_cast<uint32_t>(slab_bytes));
-      tma_load_2d(slabs + s * slab_bytes, &tma_aux, &my_aux[s], col, row);
+
+    uint4 axA[4], axB[4];  // aux chunks in flight (coalesced layout); named, never indexed dynamically, so they stay in registers
+    auto load_aux = [&](uint4 (&dst)[4], int row0, int col) {
+      const uint8_t* base = reinterpret_cast<const uint8_t*>(p.aux) +
+                            (static_cast<long long>(row0) * p.ld_aux + col) * aux_esize + jc * 16;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int row = 8 * i + rc;
+        dst[i] = (row0 + row < p.M) ? __ldg(reinterpret_cast<const uint4*>(base + static_cast<long long>(row) * p.ld_aux * aux_esize))
+                                    : make_uint4(0, 0, 0, 0);
+      }
+    };
+    // coordinates of the chunk `ahead` chunks after (w, c); false when past this CTA's last tile
+    auto chunk_after = [&](int w, int c, int ahead, int* row0, int* col) {
+      c += ahead;
+      while (c >= nchunks) { c -= nchunks; w += num_pairs; }
+      if (w >= p.total_work) return false;
+      const Work2 nt = decode_work2(p, w);
+      *row0 = tile_row0(nt);
+      *col = tile_col0(nt) + c * cw;
+      return true;
+    };
+    auto emit = [&](const CUtensorMap* map, int col, int row0, const uint4 (&q)[4]) {
+      if (p.dbg & 1) return;
+      // wait until the store issued `nout` stores ago has finished reading its slab, then reuse it
+      if (lane == 0) { if (nout == 3) tma_store_wait_read<2>(); else tma_store_wait_read<1>(); }
+      __syncwarp();
+      uint8_t* slab = slabs + oslot * 2048;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(slab + slab16_off(lane, j)) = q[j];
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        if (epi == VITK_EPI_ACCUM_F32) tma_reduce_add_2d(map, slab, col, row0);
+        else tma_store_2d(map, slab, col, row0);
+        tma_store_commit();
+      }
+      oslot = (oslot + 1 == nout) ? 0 : oslot + 1;
+    };
+    auto pack4 = [&](const float* v, uint4 (&q)[4]) {      // 32 floats → 4×16 B of bf16
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        q[j].x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+        q[j].y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+        q[j].z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+        q[j].w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+      }
     };
 
     int w = pair_id;
-    if (has_aux && w < p.total_work && lane == 0) {   // prefetch the first aux slab before any accumulator is ready
-      const Work2 it = decode_work2(p, w);
-      issue_aux(slot, tile_col0(it), tile_row0(it));
+    if (has_aux) {
+      int r0, cc;
+      if (chunk_after(w, 0, 0, &r0, &cc)) load_aux(axA, r0, cc);
+      if (chunk_after(w, 0, 1, &r0, &cc)) load_aux(axB, r0, cc);
     }
+    int axi = 0;   // 0: axA holds the current chunk's aux, 1: axB
     for (; w < p.total_work; w += num_pairs) {
       const Work2 it = decode_work2(p, w);
       const int row0 = tile_row0(it), col0 = tile_col0(it);
+      if (has_bias) {   // one coalesced read of this warp's BN/2 bias values per tile
+        for (int i = lane; i < BN / 2; i += 32) bias_s[i] = __ldg(p.bias + col0 + i);
+        __syncwarp();
+      }
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after_sync();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + col_half * (BN / 2);
 #pragma unroll 1
-      for (int c = 0; c < kChunks; ++c) {
-        const int col = col0 + c * 32;
+      for (int c = 0; c < nchunks; ++c) {
+        const int col = col0 + c * cw;
         uint32_t r[32];
-        tmem_ld_32x32(t_row + c * 32, r);
-        // while the TMEM load is in flight: make sure the slab we will write next is reusable and
-        // (aux modes) start fetching the NEXT chunk's aux tile into the next ring slot
-        const int cur = slot;
-        const int nxt = (slot + 1 == nslab) ? 0 : slot + 1;
+        if (p.dbg & 4) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) r[i] = 0;
+        } else if (out_f32) {
+          uint32_t r16[16];
+          tmem_ld_32x16(t_row + c * 16, r16);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) r[i] = r16[i];
+        } else {
+          tmem_ld_32x32(t_row + c * 32, r);
+        }
+        uint4 arow[4] = {};  // this thread's row of the aux chunk (64 B)
         if (has_aux) {
-          if (lane == 0) {
-            // slab `nxt` was last stored nslab-1 chunks ago: allow the newer stores to stay in flight
-            if (out_f32) tma_store_wait_read<1>(); else tma_store_wait_read<2>();
-            int ncol = col + 32, nrow = row0;
-            bool more = true;
-            if (c + 1 == kChunks) {       // first chunk of the next tile of this CTA
-              const int wn = w + num_pairs;
-              more = wn < p.total_work;
-              if (more) {
-                const Work2 nt = decode_work2(p, wn);
-                ncol = tile_col0(nt);
-                nrow = tile_row0(nt);
-              }
-            }
-            if (more) issue_aux(nxt, ncol, nrow);
+          uint8_t* tslab = slabs + 2 * 2048;
+          if (axi == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(tslab + slab16_off(8 * i + rc, jc)) = axA[i];
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(tslab + slab16_off(8 * i + rc, jc)) = axB[i];
           }
           __syncwarp();
-          mbar_wait(&my_aux[cur], (aux_phase_bits >> cur) & 1u);
-          aux_phase_bits ^= 1u << cur;
-        } else {
-          if (lane == 0) tma_store_wait_read<2>();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) arow[j] = *reinterpret_cast<const uint4*>(tslab + slab16_off(lane, j));
           __syncwarp();
+          int r0, cc;
+          if (chunk_after(w, c, 2, &r0, &cc)) {   // refill the registers just consumed
+            if (axi == 0) load_aux(axA, r0, cc); else load_aux(axB, r0, cc);
+          }
+          axi ^= 1;
         }
         tmem_ld_wait();
-        if (c == kChunks - 1) {           // all TMEM reads of this tile are done: hand the buffer back early
+        if (c == nchunks - 1) {           // all TMEM reads of this tile are done: hand the buffer back early
           tc_fence_before_sync();
           __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(acc_empty_leader + acc * acc_empty_stride);
+          if (lane == 0) mbar_arrive_cluster(acc_empty_leader + acc * 8);
         }
         float v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-        if (has_bias) add_bias32(p.bias, col, v);
-        uint8_t* slab = slabs + cur * slab_bytes;
-        bool second_store = false;
+        if (has_bias) {
+          const float4* b4 = reinterpret_cast<const float4*>(bias_s + c * cw);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (i < 4 || !out_f32) {
+              const float4 b = b4[i];
+              v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+            }
+          }
+        }
+        uint4 q[4];
         switch (epi) {
           case VITK_EPI_STORE_BF16:
           case VITK_EPI_BIAS_BF16:
-            st_slab16(slab, lane, v);
+            pack4(v, q);
+            emit(&tma_d, col, row0, q);
             break;
-          case VITK_EPI_BIAS_GELU_BF16: {      // d = u, d2 = gelu(u)
-            st_slab16(slab, lane, v);
+          case VITK_EPI_BIAS_GELU_BF16:        // d = u, d2 = gelu(u)
+            pack4(v, q);
+            emit(&tma_d, col, row0, q);
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
-            st_slab16(slabs + nxt * slab_bytes, lane, v);
-            second_store = true;
+            pack4(v, q);
+            emit(&tma_d2, col, row0, q);
             break;
-          }
           case VITK_EPI_BIAS_GELUG_BF16: {     // d = gelu(u), d2 = gelu'(u) (optional)
-            float gr[32];
+            float g2[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
               const GeluParts g = gelu_parts(v[i]);
-              gr[i] = fmaf(v[i], g.pdf, g.cdf);
+              g2[i] = fmaf(v[i], g.pdf, g.cdf);
               v[i] *= g.cdf;
             }
-            st_slab16(slab, lane, v);
+            pack4(v, q);
+            emit(&tma_d, col, row0, q);
             if (p.has_d2) {
-              st_slab16(slabs + nxt * slab_bytes, lane, gr);
-              second_store = true;
+              pack4(g2, q);
+              emit(&tma_d2, col, row0, q);
             }
             break;
           }
           case VITK_EPI_MUL_BF16:
           case VITK_EPI_DGELU_BF16: {
-            float a[32];
-            ld_slab16(slab, lane, a);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] *= (epi == VITK_EPI_MUL_BF16) ? a[i] : gelu_erf_grad(a[i]);
-            st_slab16(slab, lane, v);
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t wv[4] = {arow[j].x, arow[j].y, arow[j].z, arow[j].w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wv[i]));
+                v[8 * j + 2 * i] *= (epi == VITK_EPI_MUL_BF16) ? f.x : gelu_erf_grad(f.x);
+                v[8 * j + 2 * i + 1] *= (epi == VITK_EPI_MUL_BF16) ? f.y : gelu_erf_grad(f.y);
+              }
+            }
+            pack4(v, q);
+            emit(&tma_d, col, row0, q);
             break;
           }
           case VITK_EPI_BIAS_RESID_F32:
-            add_slab32(slab, lane, v);
-            st_slab32(slab, lane, v);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              q[j].x = __float_as_uint(v[4 * j] + __uint_as_float(arow[j].x));
+              q[j].y = __float_as_uint(v[4 * j + 1] + __uint_as_float(arow[j].y));
+              q[j].z = __float_as_uint(v[4 * j + 2] + __uint_as_float(arow[j].z));
+              q[j].w = __float_as_uint(v[4 * j + 3] + __uint_as_float(arow[j].w));
+            }
+            emit(&tma_d, col, row0, q);
             break;
           default:  // VITK_EPI_ACCUM_F32, VITK_EPI_STORE_F32
-            st_slab32(slab, lane, v);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              q[j] = make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
+                                __float_as_uint(v[4 * j + 3]));
+            emit(&tma_d, col, row0, q);
             break;
         }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          if (epi == VITK_EPI_ACCUM_F32) tma_reduce_add_2d(&tma_d, slab, col, row0);
-          else tma_store_2d(&tma_d, slab, col, row0);
-          tma_store_commit();
-          if (second_store) {
-            tma_store_2d(&tma_d2, slabs + nxt * slab_bytes, col, row0);
-            tma_store_commit();
-          }
-        }
-        slot = nxt;
-        if (second_store) slot = (slot + 1 == nslab) ? 0 : slot + 1;
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
@@ -399,17 +473,18 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
 }
 
 // ------------------------------------------------------------------------- host side
+// [32 rows × 64 B] output boxes (32 bf16 or 16 fp32 columns), 64-byte swizzle
 static int out_map(CUtensorMap* m, const void* base, bool f32, long long rows, long long cols, long long ld) {
   const uint64_t dims[2] = {static_cast<uint64_t>(cols), static_cast<uint64_t>(rows)};
   const uint64_t str[1] = {static_cast<uint64_t>(ld) * (f32 ? 4 : 2)};
-  const uint32_t box[2] = {32, 32};
-  return get_tensor_map(m, base, f32 ? TM_F32 : TM_BF16, 2, dims, str, box, f32 ? TM_SW128 : TM_SW64);
+  const uint32_t box[2] = {f32 ? 16u : 32u, 32u};
+  return get_tensor_map(m, base, f32 ? TM_F32 : TM_BF16, 2, dims, str, box, TM_SW64);
 }
 
 template <int BN, bool A_MN, bool B_MN>
 static int launch_gemm2(const vitk_gemm_args& a, const Gemm2Params& p, int pairs, cudaStream_t stream) {
   using Cfg = Cfg2<BN>;
-  CUtensorMap ta, tb, td, td2, taux;
+  CUtensorMap ta, tb, td, td2;
   {
     uint64_t dims[2], str[1];
     uint32_t box[2];
@@ -425,9 +500,7 @@ static int launch_gemm2(const vitk_gemm_args& a, const Gemm2Params& p, int pairs
   const bool f32_out = a.epilogue == VITK_EPI_BIAS_RESID_F32 || a.epilogue == VITK_EPI_ACCUM_F32 || a.epilogue == VITK_EPI_STORE_F32;
   if (int rc = out_map(&td, a.d, f32_out, a.M, a.N, a.ldd)) return rc;
   td2 = td;
-  taux = td;
   if (a.d2 != nullptr) { if (int rc = out_map(&td2, a.d2, false, a.M, a.N, a.ldd)) return rc; }
-  if (a.aux != nullptr) { if (int rc = out_map(&taux, a.aux, a.epilogue == VITK_EPI_BIAS_RESID_F32, a.M, a.N, a.ld_aux)) return rc; }
   auto kern = gemm2_bf16_kernel<BN, A_MN, B_MN>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
@@ -435,7 +508,7 @@ static int launch_gemm2(const vitk_gemm_args& a, const Gemm2Params& p, int pairs
     attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
   });
   if (attr_err != cudaSuccess) return cuda_error(attr_err, "cudaFuncSetAttribute(gemm2 smem)");
-  kern<<<2 * pairs, k2Threads, Cfg::kSmemBytes, stream>>>(ta, tb, td, td2, taux, p);
+  kern<<<2 * pairs, k2Threads, Cfg::kSmemBytes, stream>>>(ta, tb, td, td2, p);
   VITK_LAUNCH_CHECK("gemm2_bf16_kernel");
   return 0;
 }
@@ -451,8 +524,11 @@ static int dispatch_major2(const vitk_gemm_args& a, const Gemm2Params& p, int pa
   return set_error(VITK_EINVAL, "gemm2: tile_n 192 needs a K-major B operand");
 }
 
-// cost ∝ waves × per-tile MMA time (∝ BN), with a small penalty for the lower arithmetic intensity of
-// narrow tiles; split-K (wgrad only) multiplies the work items until one wave is full.
+// Tile choice.  Per 64-wide K block a CTA pair needs max(MMA time, shared-memory time): the MMAs take
+// 2·BN cycles, and shared memory (128 B/clk per SM) has to absorb the TMA fill and the UMMA operand
+// reads of (16 KB of A + 64·BN bytes of B) per CTA — 512 / 448 / 384 cycles for BN = 256 / 192 / 128, so
+// narrow tiles are shared-memory-bound.  cost = waves × (K blocks × that + a per-tile fill/epilogue
+// constant); split-K (wgrad only) multiplies the work items until one wave is full.
 static void choose_tiling2(const vitk_gemm_args& a, int pairs, int* bn_out, int* splits_out) {
   const long long mt = (a.M + 2 * k2BM - 1) / (2 * k2BM);
   const long long kb_total = (a.K + k2BK - 1) / k2BK;
@@ -476,8 +552,9 @@ static void choose_tiling2(const vitk_gemm_args& a, int pairs, int* bn_out, int*
     const long long kb_per = (kb_total + splits - 1) / splits;
     const long long items = tiles * ((kb_total + kb_per - 1) / kb_per);
     const long long waves = (items + pairs - 1) / pairs;
-    const double penalty = bn == 128 ? 1.12 : (bn == 192 ? 1.04 : 1.0);
-    const double cost = static_cast<double>(waves) * (kb_per * bn + 2.0 * bn /*epilogue / fill*/) * penalty;
+    const double mma = 2.0 * bn, smem = (16384.0 + 64.0 * bn) * 2.0 / 128.0;
+    const double kblock = mma > smem ? mma : smem;
+    const double cost = static_cast<double>(waves) * (kb_per * kblock + 1500.0);
     if (cost < best - 1e-9) { best = cost; *bn_out = bn; *splits_out = splits; }
   }
 }
@@ -515,6 +592,12 @@ int gemm2_try_launch(const vitk_gemm_args& a, cudaStream_t stream, bool* handled
   p.total_work = p.mn_tiles * p.k_splits;
   p.epi = a.epilogue;
   p.has_d2 = a.d2 != nullptr;
+  {
+    static const int dbg = [] { const char* e = getenv("VITK_GEMM_DBG"); return e ? atoi(e) : 0; }();
+    p.dbg = dbg;
+  }
+  p.aux = a.aux;
+  p.ld_aux = a.ld_aux;
   p.bias = a.bias;
   const int pairs = p.total_work < pairs_avail ? p.total_work : pairs_avail;
   *handled = true;

@@ -171,7 +171,9 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
   return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  // default semantics (.release.cta): only orders this CTA's prior shared-memory/TMEM traffic.  A
+  // .release.cluster here compiles to MEMBAR.ALL.GPU and stalls on every outstanding global store.
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load issued by either CTA of a pair; completion bytes are credited to the mbarrier at
 // `bar_cluster_addr` (a shared::cluster address, normally the leader CTA's barrier).
