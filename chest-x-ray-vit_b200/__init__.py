@@ -23,4 +23,7 @@ def __getattr__(name):
     if name == "GradSync":
         from .parallel import GradSync
         return GradSync
+    if name in ("modeling", "engine", "optim", "parallel"):
+        import importlib
+        return importlib.import_module(f"{__name__}.{name}")
     raise AttributeError(name)
