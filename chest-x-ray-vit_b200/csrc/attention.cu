@@ -54,166 +54,242 @@ __device__ __forceinline__ void store_row32_sw128(uint8_t* tile, int row, int co
 }
 
 // ============================================================================ forward
-constexpr int kFwdThreads = 128;
+// CTA = (128 queries, head, image); 4 softmax warps (thread = query row = TMEM lane) + 1 control warp
+// that owns TMA and MMA issue.  Two CTAs per SM.
+//   keys are consumed in sub-blocks of 64 (two per 128-key TMA tile):
+//   S_u = Q·K_uᵀ       SS-MMA (N = 64) into one of TWO S buffers in TMEM, so the tensor core computes
+//                      S_{u+1} while the softmax warps work on S_u
+//   P_u (bf16)         written back INTO the consumed S columns (two per 32-bit column) with tcgen05.st
+//   O += P_u·V_u       TS-MMA: A = P straight from TMEM, B = V rows from smem (MN-major); O accumulates
+//                      in TMEM across all sub-blocks — no per-block read-back, no P round trip via smem
+// Softmax is single-pass with a lazily updated reference maximum: probabilities are taken relative to
+// m_ref; whenever a 32-column chunk exceeds it by more than 2^16 (always on the first chunk, otherwise
+// only for extreme logits) everything accumulated so far is rescaled by 2^(old−new) ≤ 1 — exact
+// bookkeeping, m_ref cancels in O/l and in the LSE.  The last sub-block issues narrower MMAs
+// (N, K rounded up to 16 valid keys) instead of computing masked columns.
+constexpr int kFwdSoftmaxThreads = 128;
+constexpr int kFwdThreads = kFwdSoftmaxThreads + 32;
+constexpr int kSub = 64;                                   // keys per sub-block = one K/V TMA tile
+constexpr int kSubBytes = kSub * kDh * 2;                  // 8 KB
 constexpr int kFwdSmemQ = 0;
-constexpr int kFwdSmemK = kFwdSmemQ + kTileBytes;          // 2 buffers
-constexpr int kFwdSmemV = kFwdSmemK + 2 * kTileBytes;
-constexpr int kFwdSmemP = kFwdSmemV + kTileBytes;          // 2 sub-tiles
-constexpr int kFwdSmemBar = kFwdSmemP + 2 * kTileBytes;
-constexpr int kFwdSmemBytes = kFwdSmemBar + 128 + 1024;
-constexpr int kFwdTmemCols = 256;  // S: [0,128)  O-partial: [128,192)
+constexpr int kFwdSmemK = kFwdSmemQ + kTileBytes;          // 2 buffers of 64 keys
+constexpr int kFwdSmemV = kFwdSmemK + 2 * kSubBytes;       // 2 buffers
+constexpr int kFwdSmemBar = kFwdSmemV + 2 * kSubBytes;
+constexpr int kFwdSmemBytes = kFwdSmemBar + 128 + 1024;    // ≈ 49 KB → four CTAs per SM
+constexpr int kFwdTmemCols = 128;  // S/P: [0,64)   O: [64,128)
+constexpr float kLazyMaxLog2 = 16.0f;
 
-__global__ void __launch_bounds__(kFwdThreads, 2)
-attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, __nv_bfloat16* __restrict__ o, float* __restrict__ lse,
-                int T, int H, float scale_log2) {
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
+__global__ void __launch_bounds__(kFwdThreads, 4)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_kv,
+                __nv_bfloat16* __restrict__ o, float* __restrict__ lse, int T, int H, float scale_log2) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem + kFwdSmemQ;
   uint8_t* sK = smem + kFwdSmemK;
   uint8_t* sV = smem + kFwdSmemV;
-  uint8_t* sP = smem + kFwdSmemP;
   uint64_t* bar_q = reinterpret_cast<uint64_t*>(smem + kFwdSmemBar);
-  uint64_t* bar_k = bar_q + 1;  // [2]
-  uint64_t* bar_v = bar_q + 3;
-  uint64_t* bar_s = bar_q + 4;
-  uint64_t* bar_o = bar_q + 5;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_q + 6);
+  uint64_t* bar_k = bar_q + 1;      // [2] K tile landed
+  uint64_t* bar_v = bar_q + 3;      // [2] V tile landed
+  uint64_t* bar_free = bar_q + 5;   // [2] K/V buffer consumed by its P·V
+  uint64_t* bar_s = bar_q + 7;      // S ready
+  uint64_t* bar_p = bar_q + 8;      // P written by the 4 softmax warps
+  uint64_t* bar_o = bar_q + 9;      // last P·V retired
+  uint64_t* bar_pv = bar_q + 10;    // P·V(u) retired (phase u): only the rescale path waits on it
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_q + 11);
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int nkv = (T + kTile - 1) / kTile;
+  const int nsub = (T + kSub - 1) / kSub;
   const int colq = h * kDh, colk = (H + h) * kDh, colv = (2 * H + h) * kDh;
 
   if (tid == 0) {
-    tma_prefetch_desc(&tma_qkv);
-    for (int i = 0; i < 6; ++i) mbar_init(bar_q + i, 1);
+    tma_prefetch_desc(&tma_q);
+    tma_prefetch_desc(&tma_kv);
+    for (int i = 0; i < 11; ++i) mbar_init(bar_q + i, i == 8 ? 4 : 1);
     fence_mbar_init();
   }
-  if (warp == 0) tmem_alloc(tmem_slot, kFwdTmemCols);
+  if (warp == 4) tmem_alloc(tmem_slot, kFwdTmemCols);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + 128;
+  const uint32_t tmem_o = tmem_base + 64;
 
-  if (tid == 0) {
-    mbar_arrive_expect_tx(bar_q, kTileBytes);
-    tma_load_3d(sQ, &tma_qkv, bar_q, colq, qb * kTile, b);
-    mbar_arrive_expect_tx(&bar_k[0], kTileBytes);
-    tma_load_3d(sK, &tma_qkv, &bar_k[0], colk, 0, b);
-    mbar_arrive_expect_tx(bar_v, kTileBytes);
-    tma_load_3d(sV, &tma_qkv, bar_v, colv, 0, b);
-  }
-
-  constexpr uint32_t idesc_s = umma_idesc_bf16(kTile, kTile, 0, 0);
-  constexpr uint32_t idesc_pv = umma_idesc_bf16(kTile, kDh, 0, 1);
-  const uint32_t lane_field = static_cast<uint32_t>(warp * 32) << 16;
-
-  float o_acc[kDh];
+  if (warp == 4) {
+    // ------------------------------------------------------------------ control warp: TMA + MMA issue
+    if (lane == 0) {
+      auto load_kv = [&](int u) {
+        const int buf = u & 1;
+        mbar_arrive_expect_tx(&bar_k[buf], kSubBytes);
+        tma_load_3d(sK + buf * kSubBytes, &tma_kv, &bar_k[buf], colk, u * kSub, b);
+        mbar_arrive_expect_tx(&bar_v[buf], kSubBytes);
+        tma_load_3d(sV + buf * kSubBytes, &tma_kv, &bar_v[buf], colv, u * kSub, b);
+      };
+      mbar_arrive_expect_tx(bar_q, kTileBytes);
+      tma_load_3d(sQ, &tma_q, bar_q, colq, qb * kTile, b);
+      load_kv(0);
+      if (nsub > 1) load_kv(1);
+      auto sub_cols = [&](int u) { return (min(kSub, T - u * kSub) + 15) & ~15; };   // keys sub-block u needs
+      auto issue_s = [&](int u) {
+        const int buf = u & 1;
+        mbar_wait(&bar_k[buf], (u >> 1) & 1);
+        tc_fence_after_sync();
+        const uint32_t aq = smem_u32(sQ), bk = smem_u32(sK + buf * kSubBytes);
+        const uint32_t idesc_s = umma_idesc_bf16(kTile, sub_cols(u), 0, 0);
 #pragma unroll
-  for (int i = 0; i < kDh; ++i) o_acc[i] = 0.f;
-  float m_run = -INFINITY, l_run = 0.f;
-
-  for (int j = 0; j < nkv; ++j) {
-    if (tid == 0) {
-      if (j == 0) mbar_wait(bar_q, 0);
-      mbar_wait(&bar_k[j & 1], (j >> 1) & 1);
-      tc_fence_after_sync();
-      const uint32_t aq = smem_u32(sQ), bk = smem_u32(sK + (j & 1) * kTileBytes);
-#pragma unroll
-      for (int k = 0; k < kDh / 16; ++k)
-        tc_mma_bf16(tmem_s, umma_smem_desc(aq + k * 32, 0, 1024), umma_smem_desc(bk + k * 32, 0, 1024), idesc_s, k > 0);
-      tc_commit(bar_s);
-      if (j + 1 < nkv) {
-        mbar_arrive_expect_tx(&bar_k[(j + 1) & 1], kTileBytes);
-        tma_load_3d(sK + ((j + 1) & 1) * kTileBytes, &tma_qkv, &bar_k[(j + 1) & 1], colk, (j + 1) * kTile, b);
+        for (int k = 0; k < kDh / 16; ++k)
+          tc_mma_bf16(tmem_base, umma_smem_desc(aq + k * 32, 0, 1024), umma_smem_desc(bk + k * 32, 0, 1024), idesc_s, k > 0);
+        tc_commit(bar_s);
+      };
+      mbar_wait(bar_q, 0);
+      issue_s(0);
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(kTile, kDh, 0, 1);
+      for (int u = 0; u < nsub; ++u) {
+        const int buf = u & 1;
+        const uint32_t ph = (u >> 1) & 1;
+        mbar_wait(&bar_v[buf], ph);
+        mbar_wait(bar_p, u & 1);
+        tc_fence_after_sync();
+        const uint32_t bv = smem_u32(sV + buf * kSubBytes);
+        const int ksteps = sub_cols(u) / 16;
+        for (int k = 0; k < ksteps; ++k)
+          tc_mma_bf16_ts(tmem_o, tmem_base + k * 8, umma_smem_desc(bv + k * 2048, kSubBytes, 1024), idesc_pv,
+                         (u > 0 || k > 0) ? 1u : 0u);
+        tc_commit(bar_pv);
+        tc_commit(&bar_free[buf]);
+        if (u == nsub - 1) tc_commit(bar_o);
+        if (u + 1 < nsub) issue_s(u + 1);     // queued right behind P·V(u): MMAs retire in issue order
+        if (u + 2 < nsub) {                   // refill this K/V buffer once its P·V has retired
+          mbar_wait(&bar_free[buf], ph);
+          load_kv(u + 2);
+        }
       }
     }
     __syncwarp();
-    mbar_wait(bar_s, j & 1);
-    tc_fence_after_sync();
-
-    // pass 1: row maximum over the valid keys of this block
-    const int key0 = j * kTile;
-    float mx = -INFINITY;
-#pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-      uint32_t r[32];
-      tmem_ld_32x32(tmem_s + lane_field + c * 32, r);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (key0 + c * 32 + i < T) mx = fmaxf(mx, __uint_as_float(r[i]));
-    }
-    const float m_new = fmaxf(m_run, mx * scale_log2);
-    const float alpha = fast_exp2(m_run - m_new);
-    // pass 2: probabilities → bf16 P tile in smem (A operand of P·V), fp32 row sum
-    float rs = 0.f;
-#pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-      uint32_t r[32];
-      tmem_ld_32x32(tmem_s + lane_field + c * 32, r);
-      tmem_ld_wait();
-      float p[32];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const float e = fast_exp2(fmaf(__uint_as_float(r[i]), scale_log2, -m_new));
-        p[i] = (key0 + c * 32 + i < T) ? e : 0.f;
-        rs += p[i];
-      }
-      store_row32_sw128(sP, tid, c * 32, p);
-    }
-    l_run = fmaf(l_run, alpha, rs);
-    m_run = m_new;
-    fence_proxy_async_smem();
-    tc_fence_before_sync();
-    __syncthreads();
-
-    if (tid == 0) {
-      mbar_wait(bar_v, j & 1);
+  } else {
+    // ------------------------------------------------------------------ softmax warps
+    const uint32_t lane_field = static_cast<uint32_t>(warp * 32) << 16;
+    float m_ref = -INFINITY, l_run = 0.f;
+    for (int u = 0; u < nsub; ++u) {
+      const int nvalid = min(kSub, T - u * kSub);
+      const int nchunk = (nvalid + 31) >> 5;
+      const uint32_t tm_s = tmem_base + lane_field;
+      mbar_wait(bar_s, u & 1);
       tc_fence_after_sync();
-      const uint32_t ap = smem_u32(sP), bv = smem_u32(sV);
+      float rs0 = 0.f, rs1 = 0.f;
+      for (int c = 0; c < nchunk; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(tm_s + c * 32, r);
+        tmem_ld_wait();
+        const bool full = (c + 1) * 32 <= nvalid;
+        float cm = -INFINITY;
+        if (full) {
 #pragma unroll
-      for (int k = 0; k < kTile / 16; ++k)
-        tc_mma_bf16(tmem_o, umma_smem_desc(ap + (k >> 2) * kTileBytes + (k & 3) * 32, 0, 1024),
-                    umma_smem_desc(bv + k * 2048, kTileBytes, 1024), idesc_pv, k > 0);
-      tc_commit(bar_o);
+          for (int i = 0; i < 32; i += 2) cm = fmax3(cm, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i < nvalid) cm = fmaxf(cm, __uint_as_float(r[i]));
+        }
+        const float m_c = cm * scale_log2;
+        const bool fix = m_c > m_ref + kLazyMaxLog2;
+        if (__any_sync(0xffffffffu, fix)) {
+          const float m_new = fix ? m_c : m_ref;
+          const float alpha = fix ? fast_exp2(m_ref - m_new) : 1.0f;
+          l_run *= alpha;
+          rs0 *= alpha;
+          rs1 *= alpha;
+          if (u > 0) {
+            // O holds P·V of sub-blocks < u; P·V(u-1) may still be in flight
+            mbar_wait(bar_pv, (u - 1) & 1);
+            tc_fence_after_sync();
+#pragma unroll 1
+            for (int cc = 0; cc < 2; ++cc) {
+              uint32_t ro[32];
+              tmem_ld_32x32(tmem_o + lane_field + cc * 32, ro);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) ro[i] = __float_as_uint(__uint_as_float(ro[i]) * alpha);
+              tmem_st_32x32(tmem_o + lane_field + cc * 32, ro);
+            }
+          }
+#pragma unroll 1
+          for (int cc = 0; cc < c; ++cc) {
+            uint32_t pk[16];
+            tmem_ld_32x16(tm_s + cc * 16, pk);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk[i]));
+              pk[i] = pack_bf16x2(f.x * alpha, f.y * alpha);
+            }
+            tmem_st_32x16(tm_s + cc * 16, pk);
+          }
+          m_ref = m_new;
+        }
+        uint32_t pk[16];
+        if (full) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float p0 = fast_exp2(fmaf(__uint_as_float(r[2 * i]), scale_log2, -m_ref));
+            const float p1 = fast_exp2(fmaf(__uint_as_float(r[2 * i + 1]), scale_log2, -m_ref));
+            rs0 += p0;
+            rs1 += p1;
+            pk[i] = pack_bf16x2(p0, p1);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float p0 = fast_exp2(fmaf(__uint_as_float(r[2 * i]), scale_log2, -m_ref));
+            float p1 = fast_exp2(fmaf(__uint_as_float(r[2 * i + 1]), scale_log2, -m_ref));
+            if (c * 32 + 2 * i >= nvalid) p0 = 0.f;
+            if (c * 32 + 2 * i + 1 >= nvalid) p1 = 0.f;
+            rs0 += p0;
+            rs1 += p1;
+            pk[i] = pack_bf16x2(p0, p1);
+          }
+        }
+        tmem_st_32x16(tm_s + c * 16, pk);     // P overwrites S columns already consumed
+      }
+      l_run += rs0 + rs1;
+      tmem_st_wait();
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_p);
     }
-    __syncwarp();
-    mbar_wait(bar_o, j & 1);
+    mbar_wait(bar_o, 0);
     tc_fence_after_sync();
+    const int t = qb * kTile + tid;
+    const float inv = 1.0f / l_run;
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       uint32_t r[32];
       tmem_ld_32x32(tmem_o + lane_field + c * 32, r);
       tmem_ld_wait();
+      if (t < T) {
+        uint4* dst = reinterpret_cast<uint4*>(o + ((static_cast<long long>(b) * T + t) * H + h) * kDh + c * 32);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = fmaf(o_acc[c * 32 + i], alpha, __uint_as_float(r[i]));
+        for (int q = 0; q < 4; ++q) {
+          uint4 w;
+          w.x = pack_bf16x2(__uint_as_float(r[8 * q + 0]) * inv, __uint_as_float(r[8 * q + 1]) * inv);
+          w.y = pack_bf16x2(__uint_as_float(r[8 * q + 2]) * inv, __uint_as_float(r[8 * q + 3]) * inv);
+          w.z = pack_bf16x2(__uint_as_float(r[8 * q + 4]) * inv, __uint_as_float(r[8 * q + 5]) * inv);
+          w.w = pack_bf16x2(__uint_as_float(r[8 * q + 6]) * inv, __uint_as_float(r[8 * q + 7]) * inv);
+          dst[q] = w;
+        }
+      }
     }
-    tc_fence_before_sync();
-    if (tid == 0 && j + 1 < nkv) {
-      mbar_arrive_expect_tx(bar_v, kTileBytes);
-      tma_load_3d(sV, &tma_qkv, bar_v, colv, (j + 1) * kTile, b);
-    }
+    if (t < T) lse[(static_cast<long long>(b) * H + h) * T + t] = (m_ref + log2f(l_run)) * kLn2;
   }
-
-  const int t = qb * kTile + tid;
-  if (t < T) {
-    const float inv = 1.0f / l_run;
-    uint4* dst = reinterpret_cast<uint4*>(o + ((static_cast<long long>(b) * T + t) * H + h) * kDh);
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      uint4 w;
-      w.x = pack_bf16x2(o_acc[8 * q + 0] * inv, o_acc[8 * q + 1] * inv);
-      w.y = pack_bf16x2(o_acc[8 * q + 2] * inv, o_acc[8 * q + 3] * inv);
-      w.z = pack_bf16x2(o_acc[8 * q + 4] * inv, o_acc[8 * q + 5] * inv);
-      w.w = pack_bf16x2(o_acc[8 * q + 6] * inv, o_acc[8 * q + 7] * inv);
-      dst[q] = w;
-    }
-    lse[(static_cast<long long>(b) * H + h) * T + t] = (m_run + log2f(l_run)) * kLn2;
-  }
+  tc_fence_before_sync();
   __syncthreads();
-  if (warp == 0) {
+  if (warp == 4) {
     tc_fence_after_sync();
     tmem_dealloc(tmem_base, kFwdTmemCols);
   }
@@ -482,10 +558,10 @@ __global__ void __launch_bounds__(256) attn_dq_store_kernel(const float* __restr
   *reinterpret_cast<uint4*>(dqkv + row * 3 * D + col) = w;
 }
 
-static int qkv_tensor_map(CUtensorMap* m, const void* base, int64_t B, int64_t T, int64_t row_elems) {
+static int qkv_tensor_map(CUtensorMap* m, const void* base, int64_t B, int64_t T, int64_t row_elems, int rows = kTile) {
   const uint64_t dims[3] = {static_cast<uint64_t>(row_elems), static_cast<uint64_t>(T), static_cast<uint64_t>(B)};
   const uint64_t str[2] = {static_cast<uint64_t>(row_elems) * 2, static_cast<uint64_t>(T) * row_elems * 2};
-  const uint32_t box[3] = {kDh, kTile, 1};
+  const uint32_t box[3] = {kDh, static_cast<uint32_t>(rows), 1};
   return make_tensor_map_bf16(m, base, 3, dims, str, box);
 }
 
@@ -505,8 +581,9 @@ extern "C" VITK_API int vitk_attn_fwd(const void* qkv, int64_t B, int64_t T, int
   if (int rc = check_shape("attn_fwd", B, T, H)) return rc;
   VITK_REQUIRE(aligned16(qkv) && aligned16(o), VITK_EALIGN, "attn_fwd: buffers must be 16-byte aligned");
   VITK_REQUIRE(scale > 0.f, VITK_EINVAL, "attn_fwd: scale must be positive");
-  CUtensorMap tm;
+  CUtensorMap tm, tm_kv;
   if (int rc = qkv_tensor_map(&tm, qkv, B, T, 3 * H * kDh)) return rc;
+  if (int rc = qkv_tensor_map(&tm_kv, qkv, B, T, 3 * H * kDh, kSub)) return rc;
   static std::atomic<int> attr_done{0};
   if (!attr_done.load()) {
     VITK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmemBytes));
@@ -514,7 +591,7 @@ extern "C" VITK_API int vitk_attn_fwd(const void* qkv, int64_t B, int64_t T, int
   }
   const dim3 grid(static_cast<unsigned>((T + kTile - 1) / kTile), static_cast<unsigned>(H), static_cast<unsigned>(B));
   attn_fwd_kernel<<<grid, kFwdThreads, kFwdSmemBytes, static_cast<cudaStream_t>(stream)>>>(
-      tm, static_cast<__nv_bfloat16*>(o), lse, static_cast<int>(T), static_cast<int>(H), scale * kLog2e);
+      tm, tm_kv, static_cast<__nv_bfloat16*>(o), lse, static_cast<int>(T), static_cast<int>(H), scale * kLog2e);
   VITK_LAUNCH_CHECK("attn_fwd_kernel");
   return 0;
 }

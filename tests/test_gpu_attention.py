@@ -58,3 +58,21 @@ def test_attention_large_logits(ops):
     assert torch.isfinite(o.float()).all()
     assert (o.view(B, T, -1).float() - o_ref).abs().max() <= 3e-2 * o_ref.abs().max()
     assert torch.allclose(lse, lse_ref, atol=2e-2, rtol=1e-3)
+
+
+def test_attention_reference_maximum_jumps(ops):
+    """Later key blocks whose scores exceed the first block's maximum by far more than the lazy
+    threshold (2^16), including jumps past the fp32 exponent range, must rescale exactly."""
+    B, T, H = 1, 577, 1
+    g = torch.Generator().manual_seed(4)
+    qkv = torch.randn(B, T, 3, H, 64, generator=g)
+    qkv[:, :, 0] *= 3.0
+    qkv[:, 200:, 1] *= 6.0           # keys of blocks 1..4 produce much larger scores
+    qkv[:, 400:, 1] *= 8.0
+    qkv = qkv.to(dev).to(bf16)
+    do = torch.randn(B, T, H * 64, generator=g).to(dev).to(bf16)
+    o_ref, lse_ref, _ = _ref(qkv, do, 0.125)
+    o, lse = ops.attn_fwd(qkv, B, T, H, 0.125)
+    assert torch.isfinite(o.float()).all() and torch.isfinite(lse).all()
+    assert (o.view(B, T, -1).float() - o_ref).abs().max() <= 3e-2 * o_ref.abs().max()
+    assert torch.allclose(lse, lse_ref, atol=5e-2, rtol=2e-3)

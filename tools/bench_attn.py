@@ -1,0 +1,41 @@
+"""Timing of the attention kernels at the model's shape (B=16, T=577, H=12) through the C ABI."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import chest_x_ray_vit_b200 as pkg  # noqa: E402
+
+ops = pkg.ops
+B, T, H = (int(x) for x in (sys.argv[1:4] if len(sys.argv) > 3 else (16, 577, 12)))
+dev = "cuda"
+g = torch.Generator().manual_seed(0)
+qkv = torch.randn(B, T, 3, H, 64, generator=g).to(dev).to(torch.bfloat16)
+do = (torch.randn(B * T, H * 64, generator=g) * 0.1).to(dev).to(torch.bfloat16)
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+o, lse = ops.attn_fwd(qkv, B, T, H, 0.125)
+ws = torch.empty(ops.attn_bwd_workspace_bytes(B, T, H), dtype=torch.uint8, device=dev)
+dqkv = torch.empty(B * T, 3 * H * 64, dtype=torch.bfloat16, device=dev)
+
+
+def timeit(fn, reps=10):
+    for _ in range(2):
+        fn()
+    ts = []
+    for _ in range(reps):
+        flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+f_fwd = 4.0 * B * H * T * T * 64
+tf = timeit(lambda: ops.attn_fwd(qkv, B, T, H, 0.125, o=o, lse=lse))
+tb = timeit(lambda: ops.attn_bwd(qkv, o, do, lse, B, T, H, 0.125, dqkv=dqkv, workspace=ws))
+print(f"attn fwd {tf * 1e3:7.1f} us  {f_fwd / tf / 1e9:6.0f} TF/s   bwd (delta+main+dq) {tb * 1e3:7.1f} us  {2 * f_fwd / tb / 1e9:6.0f} TF/s")
