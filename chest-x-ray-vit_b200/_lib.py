@@ -61,6 +61,7 @@ _PROTOS = {
     "vitk_sumsq_f32": (C.c_int, [_p, _i64, _p, _p]),
     "vitk_clip_scale": (C.c_int, [_p, _f, _p, _p]),
     "vitk_launch_count": (C.c_int64, []),
+    "vitk_debug_timeline": (C.c_int, [_p]),
 }
 
 _lib = None

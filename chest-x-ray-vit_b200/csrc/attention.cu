@@ -25,6 +25,13 @@
 
 namespace vitk {
 
+// Optional per-phase timeline (vitk_debug_timeline): CTA (0,0,0) records clock64() stamps.
+static long long* g_timeline = nullptr;
+#define VITK_STAMP(slot)                                             \
+  do {                                                               \
+    if (tl != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0) tl[(slot)] = clock64(); \
+  } while (0)
+
 constexpr int kTile = 128;   // queries per CTA (fwd) / keys per CTA (bwd) / tokens per inner block
 constexpr int kDh = 64;
 constexpr int kTileBytes = kTile * kDh * 2;  // 16 KB
@@ -118,34 +125,46 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // broadcast marks it warp-uniform: no per-MMA elect-broadcast-retry loop
   const uint32_t tmem_o = tmem_base + 64;
 
   if (warp == 4) {
     // ------------------------------------------------------------------ control warp: TMA + MMA issue
-    if (lane == 0) {
+    // Every lane runs this loop so that descriptors and addresses stay warp-uniform (uniform registers);
+    // only the issuing instructions themselves are predicated on lane 0.  With the whole block under
+    // `if (lane == 0)` each MMA cost ~100 cycles of single-thread descriptor arithmetic + R2UR moves,
+    // several times the 32–64 cycles the MMA occupies the tensor core.
+    const bool L = lane == 0;
+    {
       auto load_kv = [&](int u) {
         const int buf = u & 1;
-        mbar_arrive_expect_tx(&bar_k[buf], kSubBytes);
-        tma_load_3d(sK + buf * kSubBytes, &tma_kv, &bar_k[buf], colk, u * kSub, b);
-        mbar_arrive_expect_tx(&bar_v[buf], kSubBytes);
-        tma_load_3d(sV + buf * kSubBytes, &tma_kv, &bar_v[buf], colv, u * kSub, b);
+        if (L) {
+          mbar_arrive_expect_tx(&bar_k[buf], kSubBytes);
+          tma_load_3d(sK + buf * kSubBytes, &tma_kv, &bar_k[buf], colk, u * kSub, b);
+          mbar_arrive_expect_tx(&bar_v[buf], kSubBytes);
+          tma_load_3d(sV + buf * kSubBytes, &tma_kv, &bar_v[buf], colv, u * kSub, b);
+        }
       };
-      mbar_arrive_expect_tx(bar_q, kTileBytes);
-      tma_load_3d(sQ, &tma_q, bar_q, colq, qb * kTile, b);
+      if (L) {
+        mbar_arrive_expect_tx(bar_q, kTileBytes);
+        tma_load_3d(sQ, &tma_q, bar_q, colq, qb * kTile, b);
+      }
       load_kv(0);
       if (nsub > 1) load_kv(1);
+      const uint64_t q_desc = umma_smem_desc(smem_u32(sQ), 0, 1024);
+      const uint64_t k_desc = umma_smem_desc(smem_u32(sK), 0, 1024);
+      const uint64_t v_desc = umma_smem_desc(smem_u32(sV), kSubBytes, 1024);
       auto sub_cols = [&](int u) { return (min(kSub, T - u * kSub) + 15) & ~15; };   // keys sub-block u needs
       auto issue_s = [&](int u) {
         const int buf = u & 1;
         mbar_wait(&bar_k[buf], (u >> 1) & 1);
         tc_fence_after_sync();
-        const uint32_t aq = smem_u32(sQ), bk = smem_u32(sK + buf * kSubBytes);
+        const uint64_t bk = k_desc + static_cast<uint64_t>(buf * (kSubBytes >> 4));
         const uint32_t idesc_s = umma_idesc_bf16(kTile, sub_cols(u), 0, 0);
 #pragma unroll
         for (int k = 0; k < kDh / 16; ++k)
-          tc_mma_bf16(tmem_base, umma_smem_desc(aq + k * 32, 0, 1024), umma_smem_desc(bk + k * 32, 0, 1024), idesc_s, k > 0);
-        tc_commit(bar_s);
+          if (L) tc_mma_bf16(tmem_base, q_desc + 2 * k, bk + 2 * k, idesc_s, k > 0);
+        if (L) tc_commit(bar_s);
       };
       mbar_wait(bar_q, 0);
       issue_s(0);
@@ -156,14 +175,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
         mbar_wait(&bar_v[buf], ph);
         mbar_wait(bar_p, u & 1);
         tc_fence_after_sync();
-        const uint32_t bv = smem_u32(sV + buf * kSubBytes);
+        const uint64_t bv = v_desc + static_cast<uint64_t>(buf * (kSubBytes >> 4));
         const int ksteps = sub_cols(u) / 16;
         for (int k = 0; k < ksteps; ++k)
-          tc_mma_bf16_ts(tmem_o, tmem_base + k * 8, umma_smem_desc(bv + k * 2048, kSubBytes, 1024), idesc_pv,
-                         (u > 0 || k > 0) ? 1u : 0u);
-        tc_commit(bar_pv);
-        tc_commit(&bar_free[buf]);
-        if (u == nsub - 1) tc_commit(bar_o);
+          if (L) tc_mma_bf16_ts(tmem_o, tmem_base + k * 8, bv + k * 128, idesc_pv, (u > 0 || k > 0) ? 1u : 0u);
+        if (L) {
+          tc_commit(bar_pv);
+          tc_commit(&bar_free[buf]);
+          if (u == nsub - 1) tc_commit(bar_o);
+        }
         if (u + 1 < nsub) issue_s(u + 1);     // queued right behind P·V(u): MMAs retire in issue order
         if (u + 2 < nsub) {                   // refill this K/V buffer once its P·V has retired
           mbar_wait(&bar_free[buf], ph);
@@ -296,17 +316,29 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
 }
 
 // ============================================================================ backward
-// delta[b,h,t] = Σ_d dO·O  (one warp per token row)
+// stats[b,h,t] = { lse·log2e, Δ = Σ_d dO·O } for t < T and { +inf, 0 } for the padding rows T ≤ t < Tpad
+// (Tpad = multiple of 128), so the main kernel reads them with unconditional aligned float4 loads and
+// padded queries get P = exp2(−inf) = 0.  One warp per token row.
 __global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __restrict__ o,
-                                                         const __nv_bfloat16* __restrict__ d_o, int BT, int T, int H,
+                                                         const __nv_bfloat16* __restrict__ d_o, const float* __restrict__ lse,
+                                                         int B, int T, int Tpad, int H, float* __restrict__ lse2,
                                                          float* __restrict__ delta) {
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);   // over B·Tpad
   const int lane = threadIdx.x & 31;
-  if (row >= BT) return;
-  const int b = row / T, t = row - b * T;
+  if (row >= B * Tpad) return;
+  const int b = row / Tpad, t = row - b * Tpad;
+  if (t >= T) {
+    for (int hh = lane; hh < H; hh += 32) {
+      const long long idx = (static_cast<long long>(b) * H + hh) * Tpad + t;
+      lse2[idx] = INFINITY;
+      delta[idx] = 0.f;
+    }
+    return;
+  }
   const int D = H * kDh;
-  const uint4* po = reinterpret_cast<const uint4*>(o + static_cast<long long>(row) * D);
-  const uint4* pd = reinterpret_cast<const uint4*>(d_o + static_cast<long long>(row) * D);
+  const long long grow = static_cast<long long>(b) * T + t;
+  const uint4* po = reinterpret_cast<const uint4*>(o + grow * D);
+  const uint4* pd = reinterpret_cast<const uint4*>(d_o + grow * D);
   for (int c0 = 0; c0 < D / 8; c0 += 32) {  // chunk c covers columns [8c, 8c+8) of head c/8
     const int c = c0 + lane;
     const bool valid = c < D / 8;
@@ -325,200 +357,268 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __
     s += __shfl_xor_sync(0xffffffffu, s, 1);
     s += __shfl_xor_sync(0xffffffffu, s, 2);
     s += __shfl_xor_sync(0xffffffffu, s, 4);
-    if (valid && (lane & 7) == 0) delta[(static_cast<long long>(b) * H + (c >> 3)) * T + t] = s;
+    if (valid && (lane & 7) == 0) {
+      const int hh = c >> 3;
+      const long long idx = (static_cast<long long>(b) * H + hh) * Tpad + t;
+      delta[idx] = s;
+      lse2[idx] = __ldg(lse + (static_cast<long long>(b) * H + hh) * T + t) * kLog2e;
+    }
   }
 }
 
-constexpr int kBwdThreads = 256;
+// backward main kernel.  CTA = (128 keys, head, image) looping over the queries in sub-blocks of 64;
+// 16 compute warps (TMEM lane quadrant = warp%4 = 32 keys, column group = warp/4 = 16 queries) + 1 control
+// warp that owns TMA and MMA issue.  Per sub-block u (buffer x = u&1):
+//   Sᵀ_x = K·Qᵀ, dPᵀ_x = V·dOᵀ       SS-MMAs (N = 64) into one of TWO score buffers in TMEM (lane = key)
+//   Pᵀ = exp2(Sᵀ·c − lse), dSᵀ = Pᵀ∘(dPᵀ − Δ)   compute warps; both are written back (bf16) INTO the warp's own
+//                                    consumed Sᵀ / dPᵀ columns with tcgen05.st, dSᵀ additionally to swizzled smem
+//   dV += Pᵀ·dO, dK += dSᵀ·Q          TS-MMAs, A straight from TMEM (no shared-memory A reads)
+//   dQ_i = dS·K                      once per 128-query block: SS-MMA, A = the dSᵀ smem tile read MN-major
+// MMAs retire in issue order, so the scores of sub-block u+2 are queued right behind dV/dK(/dQ) of u and the
+// tensor core works on buffer x while the compute warps work on buffer 1−x.  dQ is double-buffered in TMEM
+// and reduced into the fp32 accumulator one block later with per-warp TMA reduce-adds.  Keys ≥ T need no
+// masking (their dV/dK rows are never stored, their dQ contribution multiplies zero-filled K rows);
+// queries ≥ T have lse = +inf in the padded statistics, hence P = dS = 0.
+constexpr int kBwdComputeWarps = 16;
+constexpr int kBwdThreads = (kBwdComputeWarps + 1) * 32;
+constexpr int kQSub = 64;
 constexpr int kBwdSmemK = 0;
 constexpr int kBwdSmemV = kBwdSmemK + kTileBytes;
-constexpr int kBwdSmemQ = kBwdSmemV + kTileBytes;        // 2 buffers
-constexpr int kBwdSmemDO = kBwdSmemQ + 2 * kTileBytes;   // 2 buffers
-constexpr int kBwdSmemPt = kBwdSmemDO + 2 * kTileBytes;  // Pᵀ  [128 keys × 128 q]
-constexpr int kBwdSmemDSt = kBwdSmemPt + 2 * kTileBytes; // dSᵀ [128 keys × 128 q]
-constexpr int kBwdSmemStat = kBwdSmemDSt + 2 * kTileBytes;  // lse2[2][128], delta[2][128]
-constexpr int kBwdSmemBar = kBwdSmemStat + 4 * kTile * 4;
+constexpr int kBwdSmemQ = kBwdSmemV + kTileBytes;        // ring of 4 sub-tiles of 64 queries (8 KB each)
+constexpr int kBwdSmemDO = kBwdSmemQ + 2 * kTileBytes;   // ring of 4 sub-tiles
+constexpr int kBwdSmemDSt = kBwdSmemDO + 2 * kTileBytes; // dSᵀ [128 keys × 128 q], one tile per 128-query block parity
+constexpr int kBwdSmemDqS = kBwdSmemDSt + 4 * kTileBytes;   // per-warp dQ staging slabs: 16 × [32 q × 16 f32], 64 B swizzle
+constexpr int kBwdSmemBar = kBwdSmemDqS + kBwdComputeWarps * 2048;
 constexpr int kBwdSmemBytes = kBwdSmemBar + 128 + 1024;
-constexpr int kBwdTmemCols = 512;  // Sᵀ [0,128) dPᵀ [128,256) dV [256,320) dK [320,384) dQ [384,448)
+// TMEM columns: buffer x: Sᵀ/Pᵀ [128x, 128x+64), dPᵀ/dSᵀ [128x+64, 128x+128); dV [256,320) dK [320,384) dQ[2] [384,512)
+constexpr int kBwdTmemCols = 512;
 
 __global__ void __launch_bounds__(kBwdThreads, 1)
-attn_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant__ CUtensorMap tma_do,
-                const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv,
-                float* __restrict__ dq_acc, int T, int H, float scale, float scale_log2) {
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant__ CUtensorMap tma_q64,
+                const __grid_constant__ CUtensorMap tma_do64, const __grid_constant__ CUtensorMap tma_dq, const float* __restrict__ lse2, const float* __restrict__ delta,
+                __nv_bfloat16* __restrict__ dqkv, int T, int Tpad, int H, float scale, float scale_log2, long long* tl) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sK = smem + kBwdSmemK;
   uint8_t* sV = smem + kBwdSmemV;
   uint8_t* sQ = smem + kBwdSmemQ;
   uint8_t* sDO = smem + kBwdSmemDO;
-  uint8_t* sPt = smem + kBwdSmemPt;
   uint8_t* sDSt = smem + kBwdSmemDSt;
-  float* s_lse = reinterpret_cast<float*>(smem + kBwdSmemStat);  // [2][128]
-  float* s_delta = s_lse + 2 * kTile;                            // [2][128]
   uint64_t* bar_kv = reinterpret_cast<uint64_t*>(smem + kBwdSmemBar);
-  uint64_t* bar_qd = bar_kv + 1;  // [2]
-  uint64_t* bar_s = bar_kv + 3;
-  uint64_t* bar_g = bar_kv + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_kv + 5);
+  uint64_t* bar_qd = bar_kv + 1;  // [4] Q / dO sub-tile landed
+  uint64_t* bar_s = bar_kv + 5;   // [2] Sᵀ_x, dPᵀ_x ready
+  uint64_t* bar_pd = bar_kv + 7;  // [2] Pᵀ_x / dSᵀ_x written by the 16 compute warps
+  uint64_t* bar_g = bar_kv + 9;   // every MMA up to and including dQ of a 128-query block retired
+  uint64_t* bar_free = bar_kv + 10;  // [4] dV/dK of the sub-block using this Q/dO sub-tile retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_kv + 14);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int quad = warp & 3, col_half = warp >> 2;
   const int kb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int nq = (T + kTile - 1) / kTile;
+  const int nsub = (T + kQSub - 1) / kQSub;
   const int colq = h * kDh, colk = (H + h) * kDh, colv = (2 * H + h) * kDh;
   const int key0 = kb * kTile;
 
   if (tid == 0) {
     tma_prefetch_desc(&tma_qkv);
-    tma_prefetch_desc(&tma_do);
-    for (int i = 0; i < 5; ++i) mbar_init(bar_kv + i, 1);
+    tma_prefetch_desc(&tma_q64);
+    tma_prefetch_desc(&tma_do64);
+    tma_prefetch_desc(&tma_dq);
+    for (int i = 0; i < 14; ++i) mbar_init(bar_kv + i, (i == 7 || i == 8) ? kBwdComputeWarps : 1);
     fence_mbar_init();
   }
-  if (warp == 0) tmem_alloc(tmem_slot, kBwdTmemCols);
-
-  auto load_stats = [&](int i, int buf) {
-    if (tid < kTile) {
-      const int q = i * kTile + tid;
-      const long long idx = (static_cast<long long>(b) * H + h) * T + q;
-      s_lse[buf * kTile + tid] = q < T ? __ldg(lse + idx) * kLog2e : INFINITY;
-      s_delta[buf * kTile + tid] = q < T ? __ldg(delta + idx) : 0.f;
-    }
-  };
-  load_stats(0, 0);
-
+  if (warp == kBwdComputeWarps) tmem_alloc(tmem_slot, kBwdTmemCols);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tm_st = tmem_base, tm_dpt = tmem_base + 128, tm_dv = tmem_base + 256, tm_dk = tmem_base + 320,
-                 tm_dq = tmem_base + 384;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // broadcast marks it warp-uniform: no per-MMA elect-broadcast-retry loop
+  const uint32_t tm_dv = tmem_base + 256, tm_dk = tmem_base + 320, tm_dq = tmem_base + 384;
 
-  constexpr uint32_t idesc_kk = umma_idesc_bf16(kTile, kTile, 0, 0);  // Sᵀ = K·Qᵀ, dPᵀ = V·dOᵀ
-  constexpr uint32_t idesc_km = umma_idesc_bf16(kTile, kDh, 0, 1);    // dV += Pᵀ·dO, dK += dSᵀ·Q
-  constexpr uint32_t idesc_mm = umma_idesc_bf16(kTile, kDh, 1, 1);    // dQ = dS·K
-
-  auto issue_scores = [&](int buf) {  // thread 0 only
-    const uint32_t ak = smem_u32(sK), av = smem_u32(sV);
-    const uint32_t bq = smem_u32(sQ + buf * kTileBytes), bd = smem_u32(sDO + buf * kTileBytes);
-#pragma unroll
-    for (int k = 0; k < kDh / 16; ++k)
-      tc_mma_bf16(tm_st, umma_smem_desc(ak + k * 32, 0, 1024), umma_smem_desc(bq + k * 32, 0, 1024), idesc_kk, k > 0);
-#pragma unroll
-    for (int k = 0; k < kDh / 16; ++k)
-      tc_mma_bf16(tm_dpt, umma_smem_desc(av + k * 32, 0, 1024), umma_smem_desc(bd + k * 32, 0, 1024), idesc_kk, k > 0);
-    tc_commit(bar_s);
-  };
-
-  if (tid == 0) {
-    mbar_arrive_expect_tx(bar_kv, 2 * kTileBytes);
-    tma_load_3d(sK, &tma_qkv, bar_kv, colk, key0, b);
-    tma_load_3d(sV, &tma_qkv, bar_kv, colv, key0, b);
-    mbar_arrive_expect_tx(&bar_qd[0], 2 * kTileBytes);
-    tma_load_3d(sQ, &tma_qkv, &bar_qd[0], colq, 0, b);
-    tma_load_3d(sDO, &tma_do, &bar_qd[0], colq, 0, b);
-    mbar_wait(bar_kv, 0);
-    mbar_wait(&bar_qd[0], 0);
-    tc_fence_after_sync();
-    issue_scores(0);
-  }
-
-  const int key_row = quad * 32 + lane;  // TMEM lane = key (Sᵀ, dPᵀ, dV, dK) or query (dQ)
-  const bool key_valid = key0 + key_row < T;
-  const uint32_t lane_field = static_cast<uint32_t>(quad * 32) << 16;
-
-  for (int i = 0; i < nq; ++i) {
-    const int buf = i & 1;
-    if (tid == 0 && i + 1 < nq) {
-      mbar_arrive_expect_tx(&bar_qd[buf ^ 1], 2 * kTileBytes);
-      tma_load_3d(sQ + (buf ^ 1) * kTileBytes, &tma_qkv, &bar_qd[buf ^ 1], colq, (i + 1) * kTile, b);
-      tma_load_3d(sDO + (buf ^ 1) * kTileBytes, &tma_do, &bar_qd[buf ^ 1], colq, (i + 1) * kTile, b);
-    }
-    if (i + 1 < nq) load_stats(i + 1, buf ^ 1);  // visible after the __syncthreads below
-
-    __syncwarp();
-    mbar_wait(bar_s, i & 1);
-    tc_fence_after_sync();
-    const float* lse2 = s_lse + buf * kTile;
-    const float* dlt = s_delta + buf * kTile;
-#pragma unroll 1
-    for (int c = 0; c < 2; ++c) {
-      const int col0 = col_half * 64 + c * 32;
-      uint32_t rs[32], rp[32];
-      tmem_ld_32x32(tm_st + lane_field + col0, rs);
-      tmem_ld_32x32(tm_dpt + lane_field + col0, rp);
-      tmem_ld_wait();
-      float p[32], ds[32];
-#pragma unroll
-      for (int x = 0; x < 32; ++x) {
-        const float e = fast_exp2(fmaf(__uint_as_float(rs[x]), scale_log2, -lse2[col0 + x]));
-        p[x] = key_valid ? e : 0.f;
-        ds[x] = p[x] * (__uint_as_float(rp[x]) - dlt[col0 + x]);
+  if (warp == kBwdComputeWarps) {
+    // ------------------------------------------------------------------ control warp: TMA + MMA issue
+    // (all lanes run the loop so descriptors stay in uniform registers; only the issuing instructions are
+    // predicated on lane 0)
+    const bool L = lane == 0;
+    constexpr uint32_t idesc_sc = umma_idesc_bf16(kTile, kQSub, 0, 0);  // Sᵀ = K·Qᵀ, dPᵀ = V·dOᵀ (N = 64 queries)
+    constexpr uint32_t idesc_km = umma_idesc_bf16(kTile, kDh, 0, 1);    // dV += Pᵀ·dO, dK += dSᵀ·Q
+    constexpr uint32_t idesc_mm = umma_idesc_bf16(kTile, kDh, 1, 1);    // dQ = dS·K
+    constexpr uint32_t kTile16 = kTileBytes >> 4;                        // descriptor address units are 16 B
+    const uint64_t k_kmaj = umma_smem_desc(smem_u32(sK), 0, 1024);
+    const uint64_t v_kmaj = umma_smem_desc(smem_u32(sV), 0, 1024);
+    const uint64_t k_mnmaj = umma_smem_desc(smem_u32(sK), kTileBytes, 1024);
+    constexpr uint32_t kSub16 = (kQSub * 128) >> 4;                      // one 64-query sub-tile = 8 KB
+    const uint64_t q_kmaj = umma_smem_desc(smem_u32(sQ), 0, 1024);
+    const uint64_t do_kmaj = umma_smem_desc(smem_u32(sDO), 0, 1024);
+    const uint64_t q_mnmaj = umma_smem_desc(smem_u32(sQ), kQSub * 128, 1024);
+    const uint64_t do_mnmaj = umma_smem_desc(smem_u32(sDO), kQSub * 128, 1024);
+    const uint64_t dst_mnmaj = umma_smem_desc(smem_u32(sDSt), kTileBytes, 1024);
+    auto load_qd = [&](int u) {              // sub-block u → ring slot u&3
+      const int slot = u & 3;
+      if (L) {
+        mbar_arrive_expect_tx(&bar_qd[slot], 2 * kQSub * 128);
+        tma_load_3d(sQ + slot * (kQSub * 128), &tma_q64, &bar_qd[slot], colq, u * kQSub, b);
+        tma_load_3d(sDO + slot * (kQSub * 128), &tma_do64, &bar_qd[slot], colq, u * kQSub, b);
       }
-      store_row32_sw128(sPt, key_row, col0, p);
-      store_row32_sw128(sDSt, key_row, col0, ds);
-    }
-    fence_proxy_async_smem();
-    tc_fence_before_sync();
-    __syncthreads();
-
-    if (tid == 0) {
+    };
+    auto issue_scores = [&](int u) {
+      const int x = u & 1;
+      const uint64_t boff = static_cast<uint64_t>((u & 3) * kSub16);
+      mbar_wait(&bar_qd[u & 3], (u >> 2) & 1);
       tc_fence_after_sync();
-      const uint32_t apt = smem_u32(sPt), adst = smem_u32(sDSt);
-      const uint32_t bdo = smem_u32(sDO + buf * kTileBytes), bq = smem_u32(sQ + buf * kTileBytes), bk = smem_u32(sK);
+      const uint32_t t_s = tmem_base + x * 128, t_dp = t_s + 64;
 #pragma unroll
-      for (int k = 0; k < kTile / 16; ++k)   // dV[key,d] += Σ_q Pᵀ[key,q]·dO[q,d]
-        tc_mma_bf16(tm_dv, umma_smem_desc(apt + (k >> 2) * kTileBytes + (k & 3) * 32, 0, 1024),
-                    umma_smem_desc(bdo + k * 2048, kTileBytes, 1024), idesc_km, (i > 0 || k > 0) ? 1u : 0u);
+      for (int k = 0; k < kDh / 16; ++k)
+        if (L) tc_mma_bf16(t_s, k_kmaj + 2 * k, q_kmaj + boff + 2 * k, idesc_sc, k > 0);
 #pragma unroll
-      for (int k = 0; k < kTile / 16; ++k)   // dK[key,d] += Σ_q dSᵀ[key,q]·Q[q,d]
-        tc_mma_bf16(tm_dk, umma_smem_desc(adst + (k >> 2) * kTileBytes + (k & 3) * 32, 0, 1024),
-                    umma_smem_desc(bq + k * 2048, kTileBytes, 1024), idesc_km, (i > 0 || k > 0) ? 1u : 0u);
+      for (int k = 0; k < kDh / 16; ++k)
+        if (L) tc_mma_bf16(t_dp, v_kmaj + 2 * k, do_kmaj + boff + 2 * k, idesc_sc, k > 0);
+      if (L) tc_commit(&bar_s[x]);
+    };
+    if (L) {
+      mbar_arrive_expect_tx(bar_kv, 2 * kTileBytes);
+      tma_load_3d(sK, &tma_qkv, bar_kv, colk, key0, b);
+      tma_load_3d(sV, &tma_qkv, bar_kv, colv, key0, b);
+    }
+    for (int u = 0; u < 3 && u < nsub; ++u) load_qd(u);
+    mbar_wait(bar_kv, 0);
+    issue_scores(0);
+    if (nsub > 1) issue_scores(1);
+    for (int u = 0; u < nsub; ++u) {
+      const int i = u >> 1, hq = u & 1, x = u & 1;
+      const uint64_t boff = static_cast<uint64_t>((u & 3) * kSub16);
+      mbar_wait(&bar_pd[x], (u >> 1) & 1);
+      VITK_STAMP(16 * u + 0);
+      tc_fence_after_sync();
+      const uint32_t t_p = tmem_base + x * 128, t_ds = t_p + 64;
 #pragma unroll
-      for (int k = 0; k < kTile / 16; ++k)   // dQ[q,d] = Σ_key dS[q,key]·K[key,d]; A = dSᵀ tile read MN-major
-        tc_mma_bf16(tm_dq, umma_smem_desc(adst + k * 2048, kTileBytes, 1024),
-                    umma_smem_desc(bk + k * 2048, kTileBytes, 1024), idesc_mm, k > 0);
-      tc_commit(bar_g);
-      if (i + 1 < nq) {
-        mbar_wait(&bar_qd[buf ^ 1], ((i + 1) >> 1) & 1);
-        tc_fence_after_sync();
-        issue_scores(buf ^ 1);
+      for (int k = 0; k < kQSub / 16; ++k)   // dV[key,d] += Σ_q Pᵀ[key,q]·dO[q,d]; Pᵀ of column group k sits at Sᵀ column 16k
+        if (L) tc_mma_bf16_ts(tm_dv, t_p + 16 * k, do_mnmaj + boff + 128 * k, idesc_km, (u > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+      for (int k = 0; k < kQSub / 16; ++k)   // dK[key,d] += Σ_q dSᵀ[key,q]·Q[q,d]
+        if (L) tc_mma_bf16_ts(tm_dk, t_ds + 16 * k, q_mnmaj + boff + 128 * k, idesc_km, (u > 0 || k > 0) ? 1u : 0u);
+      if (L) tc_commit(&bar_free[u & 3]);
+      const bool block_done = hq == 1 || u == nsub - 1;
+      if (block_done) {
+#pragma unroll
+        for (int k = 0; k < kTile / 16; ++k)   // dQ[q,d] = Σ_key dS[q,key]·K[key,d]; A = dSᵀ smem tile read MN-major
+          if (L) tc_mma_bf16(tm_dq + (i & 1) * kDh, dst_mnmaj + static_cast<uint64_t>((i & 1) * 2 * kTile16) + 128 * k,
+                             k_mnmaj + 128 * k, idesc_mm, k > 0);
+        if (L) tc_commit(bar_g);
       }
+      VITK_STAMP(16 * u + 1);
+      if (u + 2 < nsub) issue_scores(u + 2);   // queued right behind: MMAs retire in issue order
+      VITK_STAMP(16 * u + 2);
+      if (u + 3 < nsub) {                      // refill the ring slot of sub-block u−1: its dV/dK retired a step ago
+        if (u >= 1) mbar_wait(&bar_free[(u - 1) & 3], ((u - 1) >> 2) & 1);
+        load_qd(u + 3);
+      }
+      VITK_STAMP(16 * u + 3);
     }
     __syncwarp();
-    mbar_wait(bar_g, i & 1);
-    tc_fence_after_sync();
-    {
-      uint32_t r[32];
-      tmem_ld_32x32(tm_dq + lane_field + col_half * 32, r);
+  } else {
+    // ------------------------------------------------------------------ compute warps
+    const int quad = warp & 3, cg = warp >> 2;
+    const int key_row = quad * 32 + lane;  // TMEM lane = key (Sᵀ, dPᵀ, dV, dK) or query (dQ)
+    const uint32_t lane_field = static_cast<uint32_t>(quad * 32) << 16;
+    const float* stat_lse = lse2 + (static_cast<long long>(b) * H + h) * Tpad + cg * 16;
+    const float* stat_dlt = delta + (static_cast<long long>(b) * H + h) * Tpad + cg * 16;
+    // this warp's 32 query rows × 16 head-dim columns of dQ_i: TMEM → swizzled slab → one TMA reduce-add into the
+    // fp32 accumulator (rows ≥ T are clipped by the tensor map)
+    uint8_t* dq_slab = smem + kBwdSmemDqS + warp * 2048;
+    auto reduce_dq = [&](int i) {
+      uint32_t r[16];
+      tmem_ld_32x16(tm_dq + (i & 1) * kDh + lane_field + cg * 16, r);
+      if (lane == 0) tma_store_wait_read<0>();     // previous block's reduce has finished reading the slab
+      __syncwarp();
       tmem_ld_wait();
-      const int q = i * kTile + key_row;
-      if (q < T) {
-        float* dst = dq_acc + ((static_cast<long long>(b) * T + q) * H + h) * kDh + col_half * 32;
 #pragma unroll
-        for (int x = 0; x < 8; ++x)
-          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * x),
-                       "f"(__uint_as_float(r[4 * x + 0])), "f"(__uint_as_float(r[4 * x + 1])),
-                       "f"(__uint_as_float(r[4 * x + 2])), "f"(__uint_as_float(r[4 * x + 3]))
-                       : "memory");
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<uint4*>(dq_slab + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) =
+            make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_reduce_add_3d(&tma_dq, dq_slab, h * kDh + cg * 16, i * kTile + quad * 32, b);
+        tma_store_commit();
       }
-    }
-    tc_fence_before_sync();
-  }
-
-  // dV (col_half 0) and dK·scale (col_half 1) → dqkv[b, key, 2|1, h, :]
-  {
-    const uint32_t src = (col_half == 0 ? tm_dv : tm_dk) + lane_field;
-    const float mul = col_half == 0 ? 1.0f : scale;
-    const int which = col_half == 0 ? 2 : 1;
-    const int key = key0 + key_row;
+    };
+    for (int u = 0; u < nsub; ++u) {
+      const int i = u >> 1, hq = u & 1, x = u & 1;
+      // statistics of this warp's 16 queries (padded arrays: unconditional aligned loads), issued before the wait
+      float4 l4[4], d4[4];
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint32_t r[32];
-      tmem_ld_32x32(src + c * 32, r);
+      for (int y = 0; y < 4; ++y) {
+        l4[y] = __ldg(reinterpret_cast<const float4*>(stat_lse + u * kQSub) + y);
+        d4[y] = __ldg(reinterpret_cast<const float4*>(stat_dlt + u * kQSub) + y);
+      }
+      if (warp == 0) VITK_STAMP(16 * u + 8);
+      mbar_wait(&bar_s[x], (u >> 1) & 1);
+      if (warp == 0) VITK_STAMP(16 * u + 9);
+      tc_fence_after_sync();
+      const uint32_t t_s = tmem_base + x * 128 + lane_field + cg * 16, t_dp = t_s + 64;
+      uint32_t rs[16], rp[16];
+      tmem_ld_32x16(t_s, rs);
+      tmem_ld_32x16(t_dp, rp);
       tmem_ld_wait();
+      if (warp == 0) VITK_STAMP(16 * u + 10);
+      uint32_t pk[8], dk[8];
+#pragma unroll
+      for (int y = 0; y < 4; ++y) {
+        const float lv[4] = {l4[y].x, l4[y].y, l4[y].z, l4[y].w}, dv[4] = {d4[y].x, d4[y].y, d4[y].z, d4[y].w};
+        float p[4], ds[4];
+#pragma unroll
+        for (int z = 0; z < 4; ++z) {
+          p[z] = fast_exp2(fmaf(__uint_as_float(rs[4 * y + z]), scale_log2, -lv[z]));
+          ds[z] = p[z] * (__uint_as_float(rp[4 * y + z]) - dv[z]);
+        }
+        pk[2 * y] = pack_bf16x2(p[0], p[1]);
+        pk[2 * y + 1] = pack_bf16x2(p[2], p[3]);
+        dk[2 * y] = pack_bf16x2(ds[0], ds[1]);
+        dk[2 * y + 1] = pack_bf16x2(ds[2], ds[3]);
+      }
+      if (warp == 0) VITK_STAMP(16 * u + 11);
+      tmem_st_32x8(t_s, pk);        // Pᵀ  → this warp's own (consumed) Sᵀ columns: A operand of dV
+      tmem_st_32x8(t_dp, dk);       // dSᵀ → this warp's own dPᵀ columns: A operand of dK
+      {                             // dSᵀ → smem tile [128 keys × 128 q] (two 64-query halves), A operand of dQ
+        // (double-buffered by block parity: dQ of block i may still be pending when block i+1's first half is written)
+        uint8_t* rowp = sDSt + (i & 1) * 2 * kTileBytes + hq * kTileBytes + key_row * 128;
+        *reinterpret_cast<uint4*>(rowp + (((2 * cg) ^ (key_row & 7)) << 4)) = make_uint4(dk[0], dk[1], dk[2], dk[3]);
+        *reinterpret_cast<uint4*>(rowp + (((2 * cg + 1) ^ (key_row & 7)) << 4)) = make_uint4(dk[4], dk[5], dk[6], dk[7]);
+      }
+      fence_proxy_async_smem();
+      tmem_st_wait();
+      tc_fence_before_sync();
+      __syncwarp();
+      if (warp == 0) VITK_STAMP(16 * u + 12);
+      if (lane == 0) mbar_arrive(&bar_pd[x]);
+      if (hq == 1 && i > 0) {       // dQ of the previous 128-query block: its MMAs were issued two sub-blocks ago
+        mbar_wait(bar_g, (i - 1) & 1);
+        tc_fence_after_sync();
+        reduce_dq(i - 1);
+      }
+      if (warp == 0) VITK_STAMP(16 * u + 13);
+    }
+    if (nq > 1 && (nsub & 1)) {     // an odd tail sub-block skipped the hq == 1 step that drains block nq−2
+      mbar_wait(bar_g, (nq - 2) & 1);
+      tc_fence_after_sync();
+      reduce_dq(nq - 2);
+    }
+    mbar_wait(bar_g, (nq - 1) & 1);
+    tc_fence_after_sync();
+    reduce_dq(nq - 1);
+    if (lane == 0) tma_store_wait_all<0>();
+    // dV (cg 0,1) and dK·scale (cg 2,3) → dqkv[b, key, 2|1, h, :]
+    {
+      const bool is_dv = cg < 2;
+      const int c32 = (cg & 1) * 32;
+      uint32_t r[32];
+      tmem_ld_32x32((is_dv ? tm_dv : tm_dk) + lane_field + c32, r);
+      tmem_ld_wait();
+      const float mul = is_dv ? 1.0f : scale;
+      const int key = key0 + key_row;
       if (key < T) {
-        uint4* dst = reinterpret_cast<uint4*>(dqkv + ((static_cast<long long>(b) * T + key) * 3 + which) * H * kDh +
-                                              h * kDh + c * 32);
+        uint4* dst = reinterpret_cast<uint4*>(dqkv + ((static_cast<long long>(b) * T + key) * 3 + (is_dv ? 2 : 1)) * H * kDh +
+                                              h * kDh + c32);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           uint4 w;
@@ -533,7 +633,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 0) {
+  if (warp == kBwdComputeWarps) {
     tc_fence_after_sync();
     tmem_dealloc(tmem_base, kBwdTmemCols);
   }
@@ -596,10 +696,21 @@ extern "C" VITK_API int vitk_attn_fwd(const void* qkv, int64_t B, int64_t T, int
   return 0;
 }
 
+extern "C" VITK_API int vitk_debug_timeline(void* device_buf) {
+  g_timeline = static_cast<long long*>(device_buf);
+  return 0;
+}
+
+static size_t bwd_stats_bytes(int64_t B, int64_t T, int64_t H) {
+  const int64_t Tpad = (T + kTile - 1) / kTile * kTile;
+  return (static_cast<size_t>(B) * H * Tpad * sizeof(float) + 255) / 256 * 256;
+}
+static size_t bwd_dq_bytes(int64_t B, int64_t T, int64_t H) {
+  return (static_cast<size_t>(B) * T * H * kDh * sizeof(float) + 255) / 256 * 256;
+}
+// workspace = fp32 dQ accumulator [B,T,H,64] | lse·log2e [B,H,Tpad] | Δ [B,H,Tpad]
 extern "C" VITK_API size_t vitk_attn_bwd_workspace_bytes(int64_t B, int64_t T, int64_t H) {
-  const size_t dq = static_cast<size_t>(B) * T * H * kDh * sizeof(float);
-  const size_t dl = (static_cast<size_t>(B) * H * T * sizeof(float) + 255) / 256 * 256;
-  return dq + dl;
+  return bwd_dq_bytes(B, T, H) + 2 * bwd_stats_bytes(B, T, H);
 }
 
 extern "C" VITK_API int vitk_attn_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, int64_t B, int64_t T,
@@ -610,12 +721,21 @@ extern "C" VITK_API int vitk_attn_bwd(const void* qkv, const void* o, const void
                "attn_bwd: buffers must be 16-byte aligned");
   VITK_REQUIRE(scale > 0.f, VITK_EINVAL, "attn_bwd: scale must be positive");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const size_t dq_bytes = static_cast<size_t>(B) * T * H * kDh * sizeof(float);
+  const size_t dq_bytes = bwd_dq_bytes(B, T, H);
+  const int Tpad = static_cast<int>((T + kTile - 1) / kTile * kTile);
   float* dq_acc = static_cast<float*>(workspace);
-  float* delta = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + dq_bytes);
-  CUtensorMap tm_qkv, tm_do;
+  float* lse2 = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + dq_bytes);
+  float* delta = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + dq_bytes + bwd_stats_bytes(B, T, H));
+  CUtensorMap tm_qkv, tm_q64, tm_do, tm_dq;
   if (int rc = qkv_tensor_map(&tm_qkv, qkv, B, T, 3 * H * kDh)) return rc;
-  if (int rc = qkv_tensor_map(&tm_do, d_o, B, T, H * kDh)) return rc;
+  if (int rc = qkv_tensor_map(&tm_q64, qkv, B, T, 3 * H * kDh, kQSub)) return rc;
+  if (int rc = qkv_tensor_map(&tm_do, d_o, B, T, H * kDh, kQSub)) return rc;
+  {
+    const uint64_t dims[3] = {static_cast<uint64_t>(H * kDh), static_cast<uint64_t>(T), static_cast<uint64_t>(B)};
+    const uint64_t str[2] = {static_cast<uint64_t>(H * kDh) * 4, static_cast<uint64_t>(T) * H * kDh * 4};
+    const uint32_t box[3] = {16, 32, 1};
+    if (int rc = get_tensor_map(&tm_dq, dq_acc, TM_F32, 3, dims, str, box, TM_SW64)) return rc;
+  }
   static std::atomic<int> attr_done{0};
   if (!attr_done.load()) {
     VITK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmemBytes));
@@ -623,12 +743,12 @@ extern "C" VITK_API int vitk_attn_bwd(const void* qkv, const void* o, const void
   }
   VITK_CUDA(cudaMemsetAsync(dq_acc, 0, dq_bytes, s));
   const int BT = static_cast<int>(B * T);
-  attn_delta_kernel<<<(BT + 7) / 8, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(o),
-                                                 static_cast<const __nv_bfloat16*>(d_o), BT, (int)T, (int)H, delta);
+  attn_delta_kernel<<<(static_cast<int>(B) * Tpad + 7) / 8, 256, 0, s>>>(
+      static_cast<const __nv_bfloat16*>(o), static_cast<const __nv_bfloat16*>(d_o), lse, (int)B, (int)T, Tpad, (int)H, lse2, delta);
   VITK_LAUNCH_CHECK("attn_delta_kernel");
   const dim3 grid(static_cast<unsigned>((T + kTile - 1) / kTile), static_cast<unsigned>(H), static_cast<unsigned>(B));
-  attn_bwd_kernel<<<grid, kBwdThreads, kBwdSmemBytes, s>>>(tm_qkv, tm_do, lse, delta, static_cast<__nv_bfloat16*>(dqkv),
-                                                           dq_acc, (int)T, (int)H, scale, scale * kLog2e);
+  attn_bwd_kernel<<<grid, kBwdThreads, kBwdSmemBytes, s>>>(tm_qkv, tm_q64, tm_do, tm_dq, lse2, delta, static_cast<__nv_bfloat16*>(dqkv),
+                                                           (int)T, Tpad, (int)H, scale, scale * kLog2e, g_timeline);
   VITK_LAUNCH_CHECK("attn_bwd_kernel");
   const long long n8 = static_cast<long long>(BT) * H * kDh / 8;
   attn_dq_store_kernel<<<static_cast<unsigned>((n8 + 255) / 256), 256, 0, s>>>(dq_acc, BT, (int)H, scale,

@@ -147,7 +147,10 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t cta_rank = cluster_ctarank();
+  // rank inside the CTA pair: clusters are (2,1,1), so it is the low bit of blockIdx.x.  (Reading
+  // %cluster_ctarank / mapa through inline asm hides their warp-uniformity from the compiler, which then
+  // wraps every TMA and MMA issue in an elect-broadcast-retry loop.)
+  const uint32_t cta_rank = blockIdx.x & 1u;
   const bool leader = cta_rank == 0;
   const int pair_id = blockIdx.x >> 1;
   const int num_pairs = gridDim.x >> 1;
@@ -170,24 +173,32 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   __syncthreads();
   cluster_sync_all();          // peer barriers initialised, both TMEM allocations done
   tc_fence_after_sync();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // broadcast marks it warp-uniform: no per-MMA elect-broadcast-retry loop
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int w = pair_id; w < p.total_work; w += num_pairs) {
-        const Work2 it = decode_work2(p, w);
-        const int m0 = it.m_blk * (2 * k2BM) + static_cast<int>(cta_rank) * k2BM;
-        const int n0 = it.n_blk * BN + static_cast<int>(cta_rank) * kBHalf;
-        for (int kb = it.kb_begin; kb < it.kb_end; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * Cfg::kStageBytes;
-          uint8_t* sb = sa + k2ABytes;
-          const uint32_t bar = mapa_shared(smem_u32(&full_bar[stage]), 0);
+    // All lanes run the loops of the producer and MMA warps so that stage indices, addresses and
+    // descriptors stay warp-uniform (uniform registers); only the issuing instructions are predicated on
+    // lane 0.  Under a divergent `if (lane == 0)` the compiler wraps every TMA / MMA in an
+    // elect-broadcast-retry loop.
+    const bool L = lane == 0;
+    // shared::cluster address of the leader's barrier: same offset with the pair's peer bit (bit 24) cleared
+    const uint32_t full0_leader = smem_u32(&full_bar[0]) & 0xFEFFFFFFu;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int w = pair_id; w < p.total_work; w += num_pairs) {
+      const Work2 it = decode_work2(p, w);
+      const int m0 = it.m_blk * (2 * k2BM) + static_cast<int>(cta_rank) * k2BM;
+      const int n0 = it.n_blk * BN + static_cast<int>(cta_rank) * kBHalf;
+      const int kb_begin = it.kb_begin, kb_end = it.kb_end;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * Cfg::kStageBytes;
+        uint8_t* sb = sa + k2ABytes;
+        const uint32_t bar = full0_leader + stage * 8;
+        const int k0 = kb * k2BK;
+        if (L) {
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
-          const int k0 = kb * k2BK;
           if (!A_MN) {
             tma_load_2d_pair(sa, &tma_a, bar, k0, m0);
           } else {
@@ -200,47 +211,49 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
 #pragma unroll
             for (int g = 0; g < kBHalf / 64; ++g) tma_load_2d_pair(sb + g * 8192, &tma_b, bar, n0 + g * 64, k0);
           }
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
+    __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
     if (leader) {
+      const bool L = lane == 0;
       constexpr uint32_t idesc = umma_idesc_bf16(2 * k2BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       constexpr uint32_t a_lbo = A_MN ? 8192u : 0u, b_lbo = B_MN ? 8192u : 0u;
-      constexpr uint32_t a_kstep = A_MN ? 2048u : 32u, b_kstep = B_MN ? 2048u : 32u;
+      constexpr uint32_t a_kstep = (A_MN ? 2048u : 32u) >> 4, b_kstep = (B_MN ? 2048u : 32u) >> 4;   // 16-byte units
+      const uint64_t a_desc0 = umma_smem_desc(smem_u32(smem), a_lbo, 1024);
+      const uint64_t b_desc0 = umma_smem_desc(smem_u32(smem + k2ABytes), b_lbo, 1024);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int w = pair_id; w < p.total_work; w += num_pairs) {
         const Work2 it = decode_work2(p, w);
+        const int kb_begin = it.kb_begin, kb_end = it.kb_end;
         mbar_wait(&acc_empty[acc], acc_phase ^ 1);
         tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = it.kb_begin; kb < it.kb_end; ++kb) {
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after_sync();
-          if (lane == 0) {
-            const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-            const uint32_t sb = sa + k2ABytes;
+          const uint64_t soff = static_cast<uint64_t>(stage * (Cfg::kStageBytes >> 4));
 #pragma unroll
-            for (int k = 0; k < k2BK / 16; ++k) {
-              const uint64_t ad = umma_smem_desc(sa + k * a_kstep, a_lbo, 1024);
-              const uint64_t bd = umma_smem_desc(sb + k * b_kstep, b_lbo, 1024);
-              tc_mma_bf16_pair(d_tmem, ad, bd, idesc, (kb > it.kb_begin || k > 0) ? 1u : 0u);
-            }
+          for (int k = 0; k < k2BK / 16; ++k)
+            if (L) tc_mma_bf16_pair(d_tmem, a_desc0 + soff + k * a_kstep, b_desc0 + soff + k * b_kstep, idesc,
+                                    (kb > kb_begin || k > 0) ? 1u : 0u);
+          if (L) {
             tc_commit_pair(&empty_bar[stage], 3);                         // both CTAs' producers may refill
-            if (kb == it.kb_end - 1) tc_commit_pair(&acc_full[acc], 3);   // both CTAs' epilogues may drain
+            if (kb == kb_end - 1) tc_commit_pair(&acc_full[acc], 3);   // both CTAs' epilogues may drain
           }
-          __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
     }
+    __syncwarp();
   } else if (warp >= k2FirstEpiWarp) {
     // ------------------------------------------------------------------ epilogue (both CTAs)
     // Thread = one accumulator row (TMEM lane).  A chunk is 64 bytes of output per row (32 bf16 or
@@ -262,7 +275,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     const int nchunks = (BN / 2) / cw;
     const int nout = has_aux ? 2 : 3;                      // output slabs in the ring (slab 2 transposes aux)
     const int aux_esize = out_f32 ? 4 : 2;
-    const uint32_t acc_empty_leader = mapa_shared(smem_u32(&acc_empty[0]), 0);
+    const uint32_t acc_empty_leader = smem_u32(&acc_empty[0]) & 0xFEFFFFFFu;
     int acc = 0;
     uint32_t acc_phase = 0;
     int oslot = 0;
