@@ -32,6 +32,18 @@ TRAIN_GF_PER_IMG = 332.222          # algorithmic fwd+bwd GFLOP p
 PER_GPU_BATCH = 16
 
 
+def measured_traffic():
+    """dram bytes per launch of the dominant kernel from the latest committed ncu --set full summary."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_roofline_traffic.json")))
+    if not files:
+        return None
+    try:
+        return float(json.load(open(files[-1]))["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -250,7 +262,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = t.item()
     value = world * B * K / (ms_max / 1e3)
-    last_loss = float(loss)
+    last_loss = float(loss.detach())
 
     # ---------------- end-to-end through the public API with host buffers (`e2e`)
     xh = [O.normalize_gray(x8[i].unsqueeze(1)).pin_memory() for i in range(nbuf)]
@@ -315,7 +327,7 @@ def run_ours(args):
         achieved = flops / (gms / 1e3) / 1e12
         roof = {"bound": "tensor", "kernel": "gemm_bf16_kernel (all forward/dgrad/wgrad launches of one step)",
                 "achieved": achieved, "peak": pk["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tflops_sustained"],
-                "traffic": None, "launches_per_step": n, "gemm_ms_per_step": gms, "peak_source": pk["src"] + " (sustained)",
+                "traffic": measured_traffic(), "launches_per_step": n, "gemm_ms_per_step": gms, "peak_source": pk["src"] + " (sustained)",
                 "step_tensor_frac": value / world * TRAIN_GF_PER_IMG / 1e3 / pk["tflops_sustained"]}
     if world > 1:
         dist.barrier()
