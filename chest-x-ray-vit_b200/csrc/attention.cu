@@ -125,6 +125,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
+  pdl_wait();
+  pdl_launch_dependents();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // broadcast marks it warp-uniform: no per-MMA elect-broadcast-retry loop
   const uint32_t tmem_o = tmem_base + 64;
 
@@ -323,6 +325,8 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __
                                                          const __nv_bfloat16* __restrict__ d_o, const float* __restrict__ lse,
                                                          int B, int T, int Tpad, int H, float* __restrict__ lse2,
                                                          float* __restrict__ delta) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);   // over B·Tpad
   const int lane = threadIdx.x & 31;
   if (row >= B * Tpad) return;
@@ -431,6 +435,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
+  pdl_wait();
+  pdl_launch_dependents();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // broadcast marks it warp-uniform: no per-MMA elect-broadcast-retry loop
   const uint32_t tm_dv = tmem_base + 256, tm_dk = tmem_base + 320, tm_dq = tmem_base + 384;
 
@@ -642,6 +648,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
 // dq_acc fp32 [B,T,H,64] · scale → dqkv[b,t,0,h,:] bf16
 __global__ void __launch_bounds__(256) attn_dq_store_kernel(const float* __restrict__ dq_acc, int BT, int H, float scale,
                                                             __nv_bfloat16* __restrict__ dqkv) {
+  pdl_wait();
+  pdl_launch_dependents();
   const long long i8 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;  // 8 elements each
   const int D = H * kDh;
   const long long total = static_cast<long long>(BT) * D / 8;
@@ -690,8 +698,8 @@ extern "C" VITK_API int vitk_attn_fwd(const void* qkv, int64_t B, int64_t T, int
     attr_done.store(1);
   }
   const dim3 grid(static_cast<unsigned>((T + kTile - 1) / kTile), static_cast<unsigned>(H), static_cast<unsigned>(B));
-  attn_fwd_kernel<<<grid, kFwdThreads, kFwdSmemBytes, static_cast<cudaStream_t>(stream)>>>(
-      tm, tm_kv, static_cast<__nv_bfloat16*>(o), lse, static_cast<int>(T), static_cast<int>(H), scale * kLog2e);
+  VITK_CUDA(launch_pdl(attn_fwd_kernel, grid, dim3(kFwdThreads), kFwdSmemBytes, static_cast<cudaStream_t>(stream), tm, tm_kv,
+                       static_cast<__nv_bfloat16*>(o), lse, static_cast<int>(T), static_cast<int>(H), scale * kLog2e));
   VITK_LAUNCH_CHECK("attn_fwd_kernel");
   return 0;
 }
@@ -743,16 +751,18 @@ extern "C" VITK_API int vitk_attn_bwd(const void* qkv, const void* o, const void
   }
   VITK_CUDA(cudaMemsetAsync(dq_acc, 0, dq_bytes, s));
   const int BT = static_cast<int>(B * T);
-  attn_delta_kernel<<<(static_cast<int>(B) * Tpad + 7) / 8, 256, 0, s>>>(
-      static_cast<const __nv_bfloat16*>(o), static_cast<const __nv_bfloat16*>(d_o), lse, (int)B, (int)T, Tpad, (int)H, lse2, delta);
+  VITK_CUDA(launch_pdl(attn_delta_kernel, dim3((static_cast<int>(B) * Tpad + 7) / 8), dim3(256), 0, s,
+                       static_cast<const __nv_bfloat16*>(o), static_cast<const __nv_bfloat16*>(d_o), lse, (int)B, (int)T, Tpad,
+                       (int)H, lse2, delta));
   VITK_LAUNCH_CHECK("attn_delta_kernel");
   const dim3 grid(static_cast<unsigned>((T + kTile - 1) / kTile), static_cast<unsigned>(H), static_cast<unsigned>(B));
-  attn_bwd_kernel<<<grid, kBwdThreads, kBwdSmemBytes, s>>>(tm_qkv, tm_q64, tm_do, tm_dq, lse2, delta, static_cast<__nv_bfloat16*>(dqkv),
-                                                           (int)T, Tpad, (int)H, scale, scale * kLog2e, g_timeline);
+  VITK_CUDA(launch_pdl(attn_bwd_kernel, grid, dim3(kBwdThreads), kBwdSmemBytes, s, tm_qkv, tm_q64, tm_do, tm_dq,
+                       static_cast<const float*>(lse2), static_cast<const float*>(delta), static_cast<__nv_bfloat16*>(dqkv), (int)T, Tpad,
+                       (int)H, scale, scale * kLog2e, g_timeline));
   VITK_LAUNCH_CHECK("attn_bwd_kernel");
   const long long n8 = static_cast<long long>(BT) * H * kDh / 8;
-  attn_dq_store_kernel<<<static_cast<unsigned>((n8 + 255) / 256), 256, 0, s>>>(dq_acc, BT, (int)H, scale,
-                                                                                static_cast<__nv_bfloat16*>(dqkv));
+  VITK_CUDA(launch_pdl(attn_dq_store_kernel, dim3(static_cast<unsigned>((n8 + 255) / 256)), dim3(256), 0, s,
+                       static_cast<const float*>(dq_acc), BT, (int)H, scale, static_cast<__nv_bfloat16*>(dqkv)));
   VITK_LAUNCH_CHECK("attn_dq_store_kernel");
   return 0;
 }

@@ -208,6 +208,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
+  pdl_wait();
+  pdl_launch_dependents();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // broadcast marks it warp-uniform: no per-MMA elect-broadcast-retry loop
 
   if (warp == 0) {
@@ -343,7 +345,8 @@ static int launch_gemm(const vitk_gemm_args& a, const GemmParams& p, int grid, c
     attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
   });
   if (attr_err != cudaSuccess) return cuda_error(attr_err, "cudaFuncSetAttribute(gemm smem)");
-  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  if (cudaError_t e = launch_pdl(kern, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream, ta, tb, p); e != cudaSuccess)
+    return cuda_error(e, "gemm_bf16_kernel launch");
   VITK_LAUNCH_CHECK("gemm_bf16_kernel");
   return 0;
 }

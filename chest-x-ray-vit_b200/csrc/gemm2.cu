@@ -173,6 +173,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   __syncthreads();
   cluster_sync_all();          // peer barriers initialised, both TMEM allocations done
   tc_fence_after_sync();
+  pdl_wait();                  // the previous kernel's outputs are complete; everything above overlapped its tail
+  pdl_launch_dependents();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // broadcast marks it warp-uniform: no per-MMA elect-broadcast-retry loop
 
   if (warp == 0) {
@@ -521,7 +523,8 @@ static int launch_gemm2(const vitk_gemm_args& a, const Gemm2Params& p, int pairs
     attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
   });
   if (attr_err != cudaSuccess) return cuda_error(attr_err, "cudaFuncSetAttribute(gemm2 smem)");
-  kern<<<2 * pairs, k2Threads, Cfg::kSmemBytes, stream>>>(ta, tb, td, td2, p);
+  if (cudaError_t e = launch_pdl(kern, dim3(2 * pairs), dim3(k2Threads), Cfg::kSmemBytes, stream, ta, tb, td, td2, p); e != cudaSuccess)
+    return cuda_error(e, "gemm2_bf16_kernel launch");
   VITK_LAUNCH_CHECK("gemm2_bf16_kernel");
   return 0;
 }

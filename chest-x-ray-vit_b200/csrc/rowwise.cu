@@ -96,6 +96,8 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
                                                             float eps, int M, __nv_bfloat16* __restrict__ y,
                                                             float* __restrict__ mean, float* __restrict__ rstd) {
   constexpr int D = VPL * 128;
+  pdl_wait();
+  pdl_launch_dependents();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
@@ -141,6 +143,8 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16*
                                                             __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma,
                                                             float* __restrict__ dbeta) {
   constexpr int D = VPL * 128;
+  pdl_wait();
+  pdl_launch_dependents();
   extern __shared__ float red[];  // [warps][D] reused for dγ then dβ
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   float4 gam[VPL], dg[VPL], db[VPL];
@@ -204,6 +208,8 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16*
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, int M, int N, long long ldx,
                                                           int rows_per_block, float* __restrict__ out) {
   __shared__ float red[8][256];
+  pdl_wait();
+  pdl_launch_dependents();
   const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int col = blockIdx.x * 256 + cg * 8;
   const int r0 = blockIdx.y * rows_per_block;
@@ -273,7 +279,7 @@ __global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float4* __rest
 template <int VPL>
 static int ln_fwd_launch(const float* x, long long ldx, const float* gamma, const float* beta, float eps, int M,
                          __nv_bfloat16* y, float* mean, float* rstd, cudaStream_t s) {
-  layernorm_fwd_kernel<VPL><<<(M + 7) / 8, 256, 0, s>>>(x, ldx, gamma, beta, eps, M, y, mean, rstd);
+  VITK_CUDA(launch_pdl(layernorm_fwd_kernel<VPL>, dim3((M + 7) / 8), dim3(256), 0, s, x, ldx, gamma, beta, eps, M, y, mean, rstd));
   VITK_LAUNCH_CHECK("layernorm_fwd_kernel");
   return 0;
 }
@@ -286,7 +292,8 @@ static int ln_bwd_launch(const __nv_bfloat16* dy, const float* x, long long ldx,
   const int need = (M + warps - 1) / warps;
   if (grid > need) grid = need;
   const size_t smem = static_cast<size_t>(warps) * VPL * 128 * sizeof(float);
-  layernorm_bwd_kernel<VPL><<<grid, warps * 32, smem, s>>>(dy, x, ldx, mean, rstd, gamma, dres, M, dx, dgamma, dbeta);
+  VITK_CUDA(launch_pdl(layernorm_bwd_kernel<VPL>, dim3(grid), dim3(warps * 32), smem, s, dy, x, ldx, mean, rstd, gamma, dres, M, dx,
+                       dgamma, dbeta));
   VITK_LAUNCH_CHECK("layernorm_bwd_kernel");
   return 0;
 }
@@ -377,8 +384,9 @@ extern "C" VITK_API int vitk_colsum_bf16(const void* x, int64_t M, int64_t N, in
   int rows_per_block = static_cast<int>((M + row_chunks - 1) / row_chunks);
   rows_per_block = (rows_per_block + 7) / 8 * 8;
   row_chunks = static_cast<int>((M + rows_per_block - 1) / rows_per_block);
-  colsum_bf16_kernel<<<dim3(col_blocks, row_chunks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(x), static_cast<int>(M), static_cast<int>(N), ldx, rows_per_block, out);
+  VITK_CUDA(launch_pdl(colsum_bf16_kernel, dim3(col_blocks, row_chunks), dim3(256), 0, static_cast<cudaStream_t>(stream),
+                       static_cast<const __nv_bfloat16*>(x), static_cast<int>(M), static_cast<int>(N), static_cast<long long>(ldx),
+                       rows_per_block, out));
   VITK_LAUNCH_CHECK("colsum_bf16_kernel");
   return 0;
 }
