@@ -353,13 +353,18 @@ def run_ours(args):
 
 
 def main():
+    # libraries (NCCL's version banner, …) write to fd 1: route everything to stderr and keep the real stdout for
+    # the single JSON line
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="per-GPU batch (BASELINE configs[1]: 16)")
-    ap.add_argument("--layers-per-bucket", type=int, default=1)
+    ap.add_argument("--layers-per-bucket", type=int, default=3, help="encoder layers per all-reduce bucket (3 = 85 MB; best of 1/3/6/12 at N=4)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

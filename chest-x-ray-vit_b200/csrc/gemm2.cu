@@ -580,7 +580,7 @@ static void choose_tiling2(const vitk_gemm_args& a, int pairs, int* bn_out, int*
 int gemm2_try_launch(const vitk_gemm_args& a, cudaStream_t stream, bool* handled) {
   *handled = false;
   if (a.variant == 1) return 0;
-  const bool eligible = a.epilogue != VITK_EPI_PATCH_F32 && a.N % 128 == 0 && a.max_ctas == 0 &&
+  const bool eligible = a.epilogue != VITK_EPI_PATCH_F32 && a.N % 128 == 0 && (a.max_ctas == 0 || a.max_ctas >= 2) &&
                         (a.tile_n == 0 || a.tile_n == 128 || a.tile_n == 192 || a.tile_n == 256) &&
                         !(a.tile_n == 192 && a.b_mn_major);
   if (!eligible) {
@@ -589,7 +589,8 @@ int gemm2_try_launch(const vitk_gemm_args& a, cudaStream_t stream, bool* handled
     return 0;
   }
   const int sms = num_sms();
-  const int pairs_avail = sms / 2;
+  // max_ctas leaves SMs free for a concurrent NCCL all-reduce (tile choice then balances waves over fewer pairs)
+  const int pairs_avail = (a.max_ctas > 0 && a.max_ctas < sms ? a.max_ctas : sms) / 2;
   int bn = 0, splits = 1;
   choose_tiling2(a, pairs_avail, &bn, &splits);
   if (bn == 0) {

@@ -40,7 +40,7 @@ class _Plan:
         self.steps.append((getattr(_lib.lib(), name), args, name))
 
     def gemm(self, a, b, M, N, K, d, epilogue, a_mn=False, b_mn=False, d2=None, bias=None, aux=None, rows_in=0,
-             rows_out=0, row_off=0, ldd=None, ld_aux=None, split_k=0, tile_n=0, variant=0):
+             rows_out=0, row_off=0, ldd=None, ld_aux=None, split_k=0, tile_n=0, variant=0, max_ctas=0):
         g = GemmArgs()
         g.a, g.b, g.M, g.N, g.K = a.data_ptr(), b.data_ptr(), M, N, K
         g.lda, g.ldb = a.stride(0), b.stride(0)
@@ -50,7 +50,7 @@ class _Plan:
         g.bias = None if bias is None else bias.data_ptr()
         g.aux = None if aux is None else aux.data_ptr()
         g.ld_aux = (ld_aux if ld_aux is not None else (aux.stride(0) if aux is not None else 0))
-        g.rows_in, g.rows_out, g.row_off, g.tile_n, g.max_ctas, g.variant = rows_in, rows_out, row_off, tile_n, 0, variant
+        g.rows_in, g.rows_out, g.row_off, g.tile_n, g.max_ctas, g.variant = rows_in, rows_out, row_off, tile_n, max_ctas, variant
         self._keep.append(g)
         self.gemm_flops[len(self.steps)] = 2.0 * M * N * K
         self.steps.append((_lib.lib().vitk_gemm_bf16, (C.byref(g),), "vitk_gemm_bf16"))
@@ -163,6 +163,12 @@ class Arena:
         T, P, B, M = cfg.seq_len, cfg.num_patches, self.B, self.M
         scale = 64 ** -0.5
         pl = _Plan()
+        mc = eng.comm_reserved_ctas()         # GEMMs of the backward leave SMs to the overlapped all-reduce
+        _gemm = pl.gemm
+
+        def gemm_capped(*a, **k):
+            return _gemm(*a, max_ctas=mc, **k)
+        pl.gemm = gemm_capped
         dh, dh1 = self.dh
         pl.add("vitk_fill_zero", _p(dh), dh.numel() * 2)
         pl.add("vitk_head_bwd", _p(self.h_last), _p(self.hstat[0]), _p(self.hstat[1]), _p(w["gf"]), _p(w["bf"]), _p(w["wc"]),
@@ -246,6 +252,17 @@ class Engine:
                 "g1": v(p + "layernorm_before.weight"), "b1": v(p + "layernorm_before.bias"),
                 "g2": v(p + "layernorm_after.weight"), "b2": v(p + "layernorm_after.bias")})
         return out
+
+    def comm_reserved_ctas(self) -> int:
+        """Persistent-grid cap for backward GEMMs while gradient buckets are being all-reduced: NCCL's
+        CTAs need SMs, and a CTA pair that cannot be placed at launch starts (and ends) a whole tile late.
+        0 = no cap (single GPU)."""
+        if self.grad_sync is None or getattr(self.grad_sync, "world", 1) == 1:
+            return 0
+        import os
+        reserve = int(os.environ.get("VITK_COMM_SMS", "0"))   # measured at N=4: reserving 8–32 SMs costs more than it saves
+        sms = torch.cuda.get_device_properties(self.dev).multi_processor_count
+        return max(2, sms - reserve) if reserve > 0 else 0
 
     def arena(self, B: int, train: bool) -> Arena:
         key = (B, train)

@@ -19,7 +19,7 @@ import torch.distributed as dist
 
 class GradSync:
     def __init__(self, layer_ranges: Sequence[Tuple[int, int]], rest_ranges: Sequence[Tuple[int, int]],
-                 process_group: Optional[dist.ProcessGroup] = None, layers_per_bucket: int = 1):
+                 process_group: Optional[dist.ProcessGroup] = None, layers_per_bucket: int = 3):
         self.layer_ranges = list(layer_ranges)
         self.rest_ranges = list(rest_ranges)
         self.pg = process_group
@@ -32,9 +32,11 @@ class GradSync:
         self.collectives = 0
 
     @classmethod
-    def attach(cls, model, process_group=None, layers_per_bucket: int = 1) -> "GradSync":
+    def attach(cls, model, process_group=None, layers_per_bucket: int = 3) -> "GradSync":
         gs = cls(model.layout.layer_range, model.layout.rest_ranges, process_group, layers_per_bucket)
-        model.engine().grad_sync = gs
+        eng = model.engine()
+        eng.grad_sync = gs
+        eng.arenas.clear()          # launch plans bake the SM budget left to the collective
         return gs
 
     # called by Engine.backward ------------------------------------------------

@@ -108,7 +108,7 @@ typedef struct vitk_gemm_args {
   int64_t ld_aux;
   int64_t rows_in, rows_out, row_off; /* VITK_EPI_PATCH_F32 row remap */
   int32_t tile_n;        /* 0 = library chooses; else 128, 192 or 256 */
-  int32_t max_ctas;      /* 0 = all SMs; else cap on the persistent grid (single-CTA kernel only) */
+  int32_t max_ctas;      /* 0 = all SMs; else cap on the persistent grid, leaving SMs to a concurrent collective */
   int32_t variant;       /* 0 = library chooses; 1 = single-CTA 128×N tiles (gemm.cu); 2 = CTA pair,
                             256×N tiles, TMA-store epilogue (gemm2.cu; not for VITK_EPI_PATCH_F32) */
 } vitk_gemm_args;
