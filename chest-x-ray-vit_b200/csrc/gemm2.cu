@@ -36,19 +36,22 @@ constexpr int k2EpiWarps = 8;
 constexpr int k2FirstEpiWarp = 2;
 constexpr int k2Threads = (k2FirstEpiWarp + k2EpiWarps) * 32;   // 384
 constexpr int k2ABytes = k2BM * k2BK * 2;                       // 16 KB
-constexpr int k2SlabBytes = 6144;                               // per epilogue warp: 3 slabs of [32 rows × 64 B]
-constexpr int k2StagingBytes = k2EpiWarps * k2SlabBytes;        // 48 KB
-constexpr int k2BiasBytes = k2EpiWarps * 128 * 4;                // per-warp bias slice (≤128 floats)
-constexpr int k2BarBytes = 1024;
+constexpr int k2SlabBytes = 4096;                               // per epilogue warp: 2 slabs of [32 rows × 64 B]
+constexpr int k2StagingBytes = k2EpiWarps * k2SlabBytes;        // 32 KB
+constexpr int k2BiasBytes = 2 * 2 * 128 * 4;                     // bias slice (≤128 floats) per column half × tile parity
+constexpr int k2BarBytes = 256;
 
 template <int BN>
 struct Cfg2 {
   static constexpr int kBHalfRows = BN / 2;
   static constexpr int kBBytes = kBHalfRows * k2BK * 2;
   static constexpr int kStageBytes = k2ABytes + kBBytes;
-  static constexpr int kStages = (BN == 256) ? 5 : (BN == 192 ? 6 : 7);   // 160 / 168 / 168 KB of operands in flight
+  // Operand bytes in flight are what hides the ≈3,200-cycle refill round trip (MMA retire → commit →
+  // producer wake → TMA → L2 → complete_tx on the leader → MMA wake): measured k-block cadence ≈
+  // (512 + 3200) / stages cycles, so every stage that fits in the 227 KB is used.
+  static constexpr int kStages = (BN == 256) ? 6 : (BN == 192 ? 6 : 8);   // 192 / 168 / 192 KB of operands in flight
   static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;
-  static constexpr int kSmemBytes = kStages * kStageBytes + k2StagingBytes + k2BiasBytes + k2BarBytes + 1024 /*align slack*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + k2StagingBytes + k2BiasBytes + k2BarBytes;   // no slack: smem_raw is declared 1024-aligned
 };
 
 struct Gemm2Params {
@@ -56,7 +59,8 @@ struct Gemm2Params {
   int n_tiles, mn_tiles, k_splits, kb_per_split, kb_total, total_work;
   int epi;
   int has_d2;
-  int dbg;            // VITK_GEMM_DBG experiment bits (0 in production): 1 skip stores, 2 skip aux, 4 skip TMEM loads
+  int dbg;            // VITK_GEMM_DBG experiment bits (0 in production): 1 skip stores, 2 skip aux, 4 skip TMEM loads,
+                      // 8 every CTA loads tile (0,0) (operands always L2-resident), 16 no MMAs (load pipeline only)
   const void* aux;
   long long ld_aux;
   const float* bias;
@@ -136,8 +140,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   using Cfg = Cfg2<BN>;
   constexpr int kStages = Cfg::kStages;
   constexpr int kBHalf = Cfg::kBHalfRows;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];   // 128-byte-swizzled operand tiles need 1024-byte alignment
+  uint8_t* smem = smem_raw;
   uint8_t* staging = smem + kStages * Cfg::kStageBytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + k2StagingBytes + k2BiasBytes);
   uint64_t* empty_bar = full_bar + kStages;
@@ -190,15 +194,15 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     uint32_t phase = 0;
     for (int w = pair_id; w < p.total_work; w += num_pairs) {
       const Work2 it = decode_work2(p, w);
-      const int m0 = it.m_blk * (2 * k2BM) + static_cast<int>(cta_rank) * k2BM;
-      const int n0 = it.n_blk * BN + static_cast<int>(cta_rank) * kBHalf;
+      const int m0 = (p.dbg & 8) ? 0 : it.m_blk * (2 * k2BM) + static_cast<int>(cta_rank) * k2BM;
+      const int n0 = (p.dbg & 8) ? 0 : it.n_blk * BN + static_cast<int>(cta_rank) * kBHalf;
       const int kb_begin = it.kb_begin, kb_end = it.kb_end;
       for (int kb = kb_begin; kb < kb_end; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * Cfg::kStageBytes;
         uint8_t* sb = sa + k2ABytes;
         const uint32_t bar = full0_leader + stage * 8;
-        const int k0 = kb * k2BK;
+        const int k0 = (p.dbg & 8) ? (kb & 7) * k2BK : kb * k2BK;
         if (L) {
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
           if (!A_MN) {
@@ -243,7 +247,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
           const uint64_t soff = static_cast<uint64_t>(stage * (Cfg::kStageBytes >> 4));
 #pragma unroll
           for (int k = 0; k < k2BK / 16; ++k)
-            if (L) tc_mma_bf16_pair(d_tmem, a_desc0 + soff + k * a_kstep, b_desc0 + soff + k * b_kstep, idesc,
+            if (L && !(p.dbg & 16)) tc_mma_bf16_pair(d_tmem, a_desc0 + soff + k * a_kstep, b_desc0 + soff + k * b_kstep, idesc,
                                     (kb > kb_begin || k > 0) ? 1u : 0u);
           if (L) {
             tc_commit_pair(&empty_bar[stage], 3);                         // both CTAs' producers may refill
@@ -266,8 +270,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     const int ew = warp - k2FirstEpiWarp;
     const int quad = warp & 3;                // TMEM lane quadrant (= warp id % 4)
     const int col_half = ew >> 2;
-    uint8_t* slabs = staging + ew * k2SlabBytes;            // 3 × 2 KB
-    float* bias_s = reinterpret_cast<float*>(staging + k2StagingBytes) + ew * 128;   // this warp's bias slice
+    uint8_t* slabs = staging + ew * k2SlabBytes;            // 2 × 2 KB
+    float* bias_base = reinterpret_cast<float*>(staging + k2StagingBytes) + col_half * 256;   // [tile parity][128], shared by the 4 warps of this column half
     const int epi = p.epi;
     const bool out_f32 = epi == VITK_EPI_BIAS_RESID_F32 || epi == VITK_EPI_ACCUM_F32 || epi == VITK_EPI_STORE_F32;
     const bool has_aux = !(p.dbg & 2) && (epi == VITK_EPI_BIAS_RESID_F32 || epi == VITK_EPI_MUL_BF16 || epi == VITK_EPI_DGELU_BF16);
@@ -275,7 +279,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
                                                 epi == VITK_EPI_BIAS_GELUG_BF16 || epi == VITK_EPI_BIAS_RESID_F32);
     const int cw = out_f32 ? 16 : 32;                      // chunk width in columns
     const int nchunks = (BN / 2) / cw;
-    const int nout = has_aux ? 2 : 3;                      // output slabs in the ring (slab 2 transposes aux)
+    const int nout = has_aux ? 1 : 2;                      // output slabs in the ring (the last slab transposes aux)
     const int aux_esize = out_f32 ? 4 : 2;
     const uint32_t acc_empty_leader = smem_u32(&acc_empty[0]) & 0xFEFFFFFFu;
     int acc = 0;
@@ -310,7 +314,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     auto emit = [&](const CUtensorMap* map, int col, int row0, const uint4 (&q)[4]) {
       if (p.dbg & 1) return;
       // wait until the store issued `nout` stores ago has finished reading its slab, then reuse it
-      if (lane == 0) { if (nout == 3) tma_store_wait_read<2>(); else tma_store_wait_read<1>(); }
+      if (lane == 0) { if (nout == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
       __syncwarp();
       uint8_t* slab = slabs + oslot * 2048;
 #pragma unroll
@@ -344,12 +348,24 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     for (; w < p.total_work; w += num_pairs) {
       const Work2 it = decode_work2(p, w);
       const int row0 = tile_row0(it), col0 = tile_col0(it);
-      if (has_bias) {   // one coalesced read of this warp's BN/2 bias values per tile
-        for (int i = lane; i < BN / 2; i += 32) bias_s[i] = __ldg(p.bias + col0 + i);
-        __syncwarp();
+      // This column half's BN/2 bias values: fetched before the wait, published to smem after it.  The slice is
+      // shared by the 4 quadrant warps (identical values) and double-buffered by tile parity; a warp past
+      // acc_full(t) knows every warp finished READING the bias of tile t−2, because those reads precede the
+      // acc_empty(t−2) arrivals that MMA(t) waited for.
+      float* bias_s = bias_base + acc * 128;
+      float bpre[4];
+      if (has_bias) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) bpre[i] = (lane + 32 * i < BN / 2) ? __ldg(p.bias + col0 + lane + 32 * i) : 0.f;
       }
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after_sync();
+      if (has_bias) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (lane + 32 * i < BN / 2) bias_s[lane + 32 * i] = bpre[i];
+        __syncwarp();
+      }
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + col_half * (BN / 2);
 #pragma unroll 1
       for (int c = 0; c < nchunks; ++c) {
@@ -368,7 +384,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
         }
         uint4 arow[4] = {};  // this thread's row of the aux chunk (64 B)
         if (has_aux) {
-          uint8_t* tslab = slabs + 2 * 2048;
+          uint8_t* tslab = slabs + 2048;
           if (axi == 0) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(tslab + slab16_off(8 * i + rc, jc)) = axA[i];
@@ -387,11 +403,6 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
           axi ^= 1;
         }
         tmem_ld_wait();
-        if (c == nchunks - 1) {           // all TMEM reads of this tile are done: hand the buffer back early
-          tc_fence_before_sync();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(acc_empty_leader + acc * 8);
-        }
         float v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
@@ -404,6 +415,11 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
               v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
             }
           }
+        }
+        if (c == nchunks - 1) {           // all TMEM and bias reads of this tile are done: hand the buffer back early
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(acc_empty_leader + acc * 8);
         }
         uint4 q[4];
         switch (epi) {
