@@ -55,21 +55,67 @@ def peaks():
 
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clock, power and clock-event (throttle) reasons of one GPU every ~10 ms from a background
+    thread through NVML (what `nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons.*` reads) while the
+    timed region runs; falls back to an nvidia-smi subprocess when pynvml is unavailable."""
+    REASONS = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "sw_power_cap": 0x4,
+               "hw_power_brake_slowdown": 0x80}
 
     def __init__(self, gpu_index: int):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        import threading
+        self.samples = []
+        self.stop_flag = False
+        self.mode = None
         self.proc = None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                                          "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
-        except OSError:
-            pass
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[gpu_index]) if vis and vis.split(",")[gpu_index].strip().isdigit() else gpu_index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.mode = "nvml"
+            self.t = threading.Thread(target=self._loop, daemon=True)
+            self.t.start()
+        except Exception:
+            q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+            self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+            try:
+                self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "20",
+                                              "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+                self.mode = "smi"
+            except OSError:
+                pass
+
+    def _loop(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                try:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.samples.append((sm, pw, rs))
+            except Exception:
+                pass
+            time.sleep(0.01)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        if self.mode == "nvml":
+            self.stop_flag = True
+            self.t.join(timeout=2)
+            if not self.samples:
+                return {"sm_mhz": None, "sm_max_mhz": self.max_sm, "reasons": ["no samples"]}
+            reasons = sorted(n for n, bit in self.REASONS.items() if any(r & bit for _, _, r in self.samples))
+            return {"sm_mhz": statistics.median(s for s, _, _ in self.samples), "sm_max_mhz": self.max_sm,
+                    "power_w_max": max(p for _, p, _ in self.samples), "samples": len(self.samples), "reasons": reasons,
+                    "source": "NVML, 10 ms period, during the timed region"}
+        if self.mode != "smi":
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml and nvidia-smi unavailable"]}
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
@@ -80,14 +126,14 @@ class ClockSampler:
         os.unlink(self.f.name)
         if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        sm = [float(r[1]) for r in rows]
         reasons = set()
         for r in rows:
             for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
                 if r[col].strip().lower() == "active":
                     reasons.add(name)
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": float(rows[0][2]), "power_w_max": max(float(r[3]) for r in rows),
-                "samples": len(rows), "reasons": sorted(reasons)}
+        return {"sm_mhz": statistics.median(float(r[1]) for r in rows), "sm_max_mhz": float(rows[0][2]),
+                "power_w_max": max(float(r[3]) for r in rows), "samples": len(rows), "reasons": sorted(reasons),
+                "source": "nvidia-smi -lms 20 during the timed region"}
 
 
 # ----------------------------------------------------------------------------- reference arm (CPU)

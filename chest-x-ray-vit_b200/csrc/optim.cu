@@ -10,9 +10,9 @@
 namespace vitk {
 
 __global__ void __launch_bounds__(256)
-adamw_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m, float4* __restrict__ v,
+adamw_kernel(float4* __restrict__ p, float4* __restrict__ g, float4* __restrict__ m, float4* __restrict__ v,
              uint2* __restrict__ p16, long long n4, float lr, float b1, float b2, float eps, float wd, float bc1,
-             float rsqrt_bc2, const float* __restrict__ grad_scale) {
+             float rsqrt_bc2, const float* __restrict__ grad_scale, int zero_grad) {
   const float gs = grad_scale ? __ldg(grad_scale) : 1.0f;
   const float step = lr / bc1, decay = 1.0f - lr * wd;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
@@ -30,6 +30,7 @@ adamw_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __res
       pa[k] = fmaf(-step, __fdiv_rn(ma[k], denom), pa[k] * decay);
     }
     p[i] = pp; m[i] = mm; v[i] = vv;
+    if (zero_grad) g[i] = make_float4(0.f, 0.f, 0.f, 0.f);   // next backward accumulates into a clean buffer: no memset pass
     if (p16) {
       __nv_bfloat162 lo = __floats2bfloat162_rn(pp.x, pp.y), hi = __floats2bfloat162_rn(pp.z, pp.w);
       p16[i] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
@@ -66,9 +67,9 @@ __global__ void clip_scale_kernel(const float* sumsq, float max_norm, float* sca
 
 using namespace vitk;
 
-extern "C" VITK_API int vitk_adamw(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, float lr,
+extern "C" VITK_API int vitk_adamw(float* p, float* g, float* m, float* v, void* p_bf16, int64_t n, float lr,
                                    float beta1, float beta2, float eps, float weight_decay, float bias_corr1,
-                                   float bias_corr2, const float* grad_scale, vitk_stream_t stream) {
+                                   float bias_corr2, const float* grad_scale, int zero_grad, vitk_stream_t stream) {
   VITK_REQUIRE(p && g && m && v && n > 0 && n % 4 == 0, VITK_EINVAL, "adamw: n must be a positive multiple of 4");
   VITK_REQUIRE(aligned16(p) && aligned16(g) && aligned16(m) && aligned16(v) && (reinterpret_cast<uintptr_t>(p_bf16) & 7) == 0,
                VITK_EALIGN, "adamw: buffers must be 16-byte aligned");
@@ -78,9 +79,9 @@ extern "C" VITK_API int vitk_adamw(float* p, const float* g, float* m, float* v,
   const long long cap = static_cast<long long>(num_sms()) * 8;
   if (blocks > cap) blocks = cap;
   adamw_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<float4*>(p), reinterpret_cast<const float4*>(g), reinterpret_cast<float4*>(m),
+      reinterpret_cast<float4*>(p), reinterpret_cast<float4*>(g), reinterpret_cast<float4*>(m),
       reinterpret_cast<float4*>(v), static_cast<uint2*>(p_bf16), n4, lr, beta1, beta2, eps, weight_decay, bias_corr1,
-      1.0f / sqrtf(bias_corr2), grad_scale);
+      1.0f / sqrtf(bias_corr2), grad_scale, zero_grad);
   VITK_LAUNCH_CHECK("adamw_kernel");
   return 0;
 }

@@ -141,18 +141,19 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16*
                                                             const float* __restrict__ rstd, const float* __restrict__ gamma,
                                                             const __nv_bfloat16* __restrict__ dres, int M,
                                                             __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma,
-                                                            float* __restrict__ dbeta) {
+                                                            float* __restrict__ dbeta, float* __restrict__ dxsum) {
   constexpr int D = VPL * 128;
   pdl_wait();
   pdl_launch_dependents();
-  extern __shared__ float red[];  // [warps][D] reused for dγ then dβ
+  extern __shared__ float red[];  // [warps][D] reused for dγ, dβ and Σdx
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  float4 gam[VPL], dg[VPL], db[VPL];
+  float4 gam[VPL], dg[VPL], db[VPL], dsx[VPL];
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
     gam[i] = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * i);
     dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    dsx[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   for (int row = blockIdx.x * nwarps + warp; row < M; row += gridDim.x * nwarps) {
     const float mu = __ldg(mean + row), r = __ldg(rstd + row);
@@ -184,16 +185,22 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16*
         const float2 a = unbf2(w.x), b = unbf2(w.y);
         o0 += a.x; o1 += a.y; o2 += b.x; o3 += b.y;
       }
-      dxr[lane + 32 * i] = make_uint2(bf2(o0, o1), bf2(o2, o3));
+      const uint2 packed = make_uint2(bf2(o0, o1), bf2(o2, o3));
+      dxr[lane + 32 * i] = packed;
+      if (dxsum != nullptr) {   // column sums of the bf16 values actually stored (what the wgrad GEMM will read)
+        const float2 s01 = unbf2(packed.x), s23 = unbf2(packed.y);
+        dsx[i].x += s01.x; dsx[i].y += s01.y; dsx[i].z += s23.x; dsx[i].w += s23.y;
+      }
     }
   }
   // block reduction of the per-warp partials
   float4* red4 = reinterpret_cast<float4*>(red);
-  for (int pass = 0; pass < 2; ++pass) {
+  const int npass = dxsum != nullptr ? 3 : 2;
+  for (int pass = 0; pass < npass; ++pass) {
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) red4[warp * (D / 4) + lane + 32 * i] = pass == 0 ? dg[i] : db[i];
+    for (int i = 0; i < VPL; ++i) red4[warp * (D / 4) + lane + 32 * i] = pass == 0 ? dg[i] : (pass == 1 ? db[i] : dsx[i]);
     __syncthreads();
-    float* dst = pass == 0 ? dgamma : dbeta;
+    float* dst = pass == 0 ? dgamma : (pass == 1 ? dbeta : dxsum);
     for (int c = threadIdx.x; c < D; c += blockDim.x) {
       float s = 0.f;
       for (int w = 0; w < nwarps; ++w) s += red[w * D + c];
@@ -286,14 +293,14 @@ static int ln_fwd_launch(const float* x, long long ldx, const float* gamma, cons
 template <int VPL>
 static int ln_bwd_launch(const __nv_bfloat16* dy, const float* x, long long ldx, const float* mean, const float* rstd,
                          const float* gamma, const __nv_bfloat16* dres, int M, __nv_bfloat16* dx, float* dgamma,
-                         float* dbeta, cudaStream_t s) {
+                         float* dbeta, float* dxsum, cudaStream_t s) {
   const int warps = 8;
-  int grid = num_sms() * 2;
+  int grid = num_sms() * 3;
   const int need = (M + warps - 1) / warps;
   if (grid > need) grid = need;
   const size_t smem = static_cast<size_t>(warps) * VPL * 128 * sizeof(float);
   VITK_CUDA(launch_pdl(layernorm_bwd_kernel<VPL>, dim3(grid), dim3(warps * 32), smem, s, dy, x, ldx, mean, rstd, gamma, dres, M, dx,
-                       dgamma, dbeta));
+                       dgamma, dbeta, dxsum));
   VITK_LAUNCH_CHECK("layernorm_bwd_kernel");
   return 0;
 }
@@ -354,7 +361,7 @@ extern "C" VITK_API int vitk_layernorm_fwd(const float* x, int64_t ldx, const fl
 
 extern "C" VITK_API int vitk_layernorm_bwd(const void* dy, const float* x, int64_t ldx, const float* mean, const float* rstd,
                                   const float* gamma, const void* dres, int64_t M, int64_t D, void* dx, float* dgamma,
-                                  float* dbeta, vitk_stream_t stream) {
+                                  float* dbeta, float* dxsum, vitk_stream_t stream) {
   VITK_REQUIRE(dy && x && mean && rstd && gamma && dx && dgamma && dbeta, VITK_EINVAL, "layernorm_bwd: NULL argument");
   VITK_REQUIRE(M > 0 && M < (1ll << 31), VITK_EINVAL, "layernorm_bwd: bad M");
   VITK_REQUIRE(ldx >= D && ldx % 4 == 0 && aligned16(x) && aligned16(dy) && aligned16(dx) && aligned16(gamma) &&
@@ -365,11 +372,11 @@ extern "C" VITK_API int vitk_layernorm_bwd(const void* dy, const float* x, int64
   const __nv_bfloat16* rr = static_cast<const __nv_bfloat16*>(dres);
   __nv_bfloat16* dxx = static_cast<__nv_bfloat16*>(dx);
   switch (D) {
-    case 128: return ln_bwd_launch<1>(dyy, x, ldx, mean, rstd, gamma, rr, (int)M, dxx, dgamma, dbeta, s);
-    case 256: return ln_bwd_launch<2>(dyy, x, ldx, mean, rstd, gamma, rr, (int)M, dxx, dgamma, dbeta, s);
-    case 512: return ln_bwd_launch<4>(dyy, x, ldx, mean, rstd, gamma, rr, (int)M, dxx, dgamma, dbeta, s);
-    case 768: return ln_bwd_launch<6>(dyy, x, ldx, mean, rstd, gamma, rr, (int)M, dxx, dgamma, dbeta, s);
-    case 1024: return ln_bwd_launch<8>(dyy, x, ldx, mean, rstd, gamma, rr, (int)M, dxx, dgamma, dbeta, s);
+    case 128: return ln_bwd_launch<1>(dyy, x, ldx, mean, rstd, gamma, rr, (int)M, dxx, dgamma, dbeta, dxsum, s);
+    case 256: return ln_bwd_launch<2>(dyy, x, ldx, mean, rstd, gamma, rr, (int)M, dxx, dgamma, dbeta, dxsum, s);
+    case 512: return ln_bwd_launch<4>(dyy, x, ldx, mean, rstd, gamma, rr, (int)M, dxx, dgamma, dbeta, dxsum, s);
+    case 768: return ln_bwd_launch<6>(dyy, x, ldx, mean, rstd, gamma, rr, (int)M, dxx, dgamma, dbeta, dxsum, s);
+    case 1024: return ln_bwd_launch<8>(dyy, x, ldx, mean, rstd, gamma, rr, (int)M, dxx, dgamma, dbeta, dxsum, s);
     default: return set_error(VITK_EINVAL, "layernorm_bwd: hidden size %lld unsupported", (long long)D);
   }
 }

@@ -174,20 +174,24 @@ class Arena:
         pl.add("vitk_head_bwd", _p(self.h_last), _p(self.hstat[0]), _p(self.hstat[1]), _p(w["gf"]), _p(w["bf"]), _p(w["wc"]),
                B, T, D, Cn, _p(self.dlogits if from_loss else self.dlogits_in), _p(self.dloss) if from_loss else None,
                _p(dh), _p(g["wc"]), _p(g["bc"]), _p(g["gf"]), _p(g["bf"]))
+        # Bias gradients of the two D-wide linears (fc2, out-proj) are column sums of the residual-stream gradients
+        # that the LayerNorm backward kernels produce anyway, so those kernels emit them (dxsum): dh entering layer
+        # l is the dx of layer l+1's LN1 backward (→ fc2 bias of layer l), dh1 is the dx of layer l's LN2 backward
+        # (→ out-proj bias of layer l).  Only the top layer's fc2 bias needs a separate pass (its dh comes from the head).
         for l in reversed(range(L)):
             lw, lg, st = w["layers"][l], g["layers"][l], self.st[l]
             # MLP
             pl.gemm(dh, self.a[l], D, Fi, M, lg["w2"], EPI_ACCUM_F32, a_mn=True, b_mn=True)
-            pl.add("vitk_colsum_bf16", _p(dh), M, D, D, _p(lg["bf2"]))
+            if l == L - 1:
+                pl.add("vitk_colsum_bf16", _p(dh), M, D, D, _p(lg["bf2"]))
             pl.gemm(dh, lw["w2_16"], M, Fi, D, self.du, EPI_MUL_BF16, b_mn=True, aux=self.gp[l])
             pl.gemm(self.du, self.n2[l], Fi, D, M, lg["w1"], EPI_ACCUM_F32, a_mn=True, b_mn=True)
             pl.add("vitk_colsum_bf16", _p(self.du), M, Fi, Fi, _p(lg["bf1"]))
             pl.gemm(self.du, lw["w1_16"], M, D, Fi, self.dn, EPI_STORE_BF16, b_mn=True)
             pl.add("vitk_layernorm_bwd", _p(self.dn), _p(self.h1[l]), D, _p(st[2]), _p(st[3]), _p(lw["g2"]), _p(dh), M, D,
-                   _p(dh1), _p(lg["g2"]), _p(lg["b2"]))
+                   _p(dh1), _p(lg["g2"]), _p(lg["b2"]), _p(lg["bo"]))
             # attention
             pl.gemm(dh1, self.o[l], D, D, M, lg["wo"], EPI_ACCUM_F32, a_mn=True, b_mn=True)
-            pl.add("vitk_colsum_bf16", _p(dh1), M, D, D, _p(lg["bo"]))
             pl.gemm(dh1, lw["wo16"], M, D, D, self.do, EPI_STORE_BF16, b_mn=True)
             pl.add("vitk_attn_bwd", _p(self.qkv[l]), _p(self.o[l]), _p(self.do), _p(self.lse[l]), B, T, H, scale,
                    _p(self.dqkv), _p(self.attn_ws))
@@ -195,7 +199,7 @@ class Arena:
             pl.add("vitk_colsum_bf16", _p(self.dqkv), M, 3 * D, 3 * D, _p(lg["bqkv"]))
             pl.gemm(self.dqkv, lw["wqkv16"], M, D, 3 * D, self.dn, EPI_STORE_BF16, b_mn=True)
             pl.add("vitk_layernorm_bwd", _p(self.dn), _p(self.h[l]), D, _p(st[0]), _p(st[1]), _p(lw["g1"]), _p(dh1), M, D,
-                   _p(dh), _p(lg["g1"]), _p(lg["b1"]))
+                   _p(dh), _p(lg["g1"]), _p(lg["b1"]), _p(g["layers"][l - 1]["bf2"]) if l > 0 else None)
             pl.call(lambda l=l: eng._layer_grads_ready(l))
         pl.add("vitk_embed_bwd", _p(dh), B, T, D, _p(g["pos"]), _p(g["cls"]), _p(g["bp"]), _p(self.dpatch))
         pl.gemm(self.dpatch, self.apatch, D, 768, B * P, g["wp"], EPI_ACCUM_F32, a_mn=True, b_mn=True)

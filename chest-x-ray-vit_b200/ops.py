@@ -75,14 +75,14 @@ def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps:
     return y, mean, rstd
 
 
-def layernorm_bwd(dy, x, mean, rstd, gamma, dres, dgamma, dbeta, dx=None):
-    """dx = dres + LNbwd(dy) (bf16); dgamma/dbeta (fp32) are accumulated."""
+def layernorm_bwd(dy, x, mean, rstd, gamma, dres, dgamma, dbeta, dx=None, dxsum=None):
+    """dx = dres + LNbwd(dy) (bf16); dgamma/dbeta (fp32) are accumulated; dxsum (optional) += Σ_rows dx."""
     M, D = x.shape
     if dx is None:
         dx = torch.empty((M, D), dtype=bf16, device=x.device)
     _lib.check(_lib.lib().vitk_layernorm_bwd(dy.data_ptr(), x.data_ptr(), x.stride(0), mean.data_ptr(), rstd.data_ptr(),
                                               gamma.data_ptr(), _ptr(dres), M, D, dx.data_ptr(), dgamma.data_ptr(),
-                                              dbeta.data_ptr(), _stream()), "layernorm_bwd")
+                                              dbeta.data_ptr(), _ptr(dxsum), _stream()), "layernorm_bwd")
     return dx
 
 
@@ -184,9 +184,9 @@ def fill_zero(t: torch.Tensor):
 
 
 def adamw(p, g, m, v, p16, n: int, lr: float, beta1: float, beta2: float, eps: float, wd: float, bc1: float, bc2: float,
-          grad_scale: Optional[torch.Tensor] = None):
+          grad_scale: Optional[torch.Tensor] = None, zero_grad: bool = False):
     _lib.check(_lib.lib().vitk_adamw(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), _ptr(p16), n, lr, beta1, beta2,
-                                      eps, wd, bc1, bc2, _ptr(grad_scale), _stream()), "adamw")
+                                      eps, wd, bc1, bc2, _ptr(grad_scale), int(zero_grad), _stream()), "adamw")
 
 
 def sumsq(x: torch.Tensor, out: torch.Tensor):

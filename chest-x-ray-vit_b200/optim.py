@@ -24,6 +24,10 @@ class VitkAdamW(torch.optim.Optimizer):
                          dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         self.model = model
         self.max_grad_norm = max_grad_norm
+        # step() also clears the flat gradient buffer (same pass over it), so zero_grad() after step() is free:
+        # param.grad stay bound to the (now zero) views and the next backward needs no memset.
+        self.fused_zero_grad = True
+        self._grads_clean = False
         self._step = 0
         self._m = self._v = self._ss = self._scale = None
 
@@ -57,15 +61,24 @@ class VitkAdamW(torch.optim.Optimizer):
         bc1, bc2 = 1.0 - b1 ** t, 1.0 - b2 ** t
         ge, de, n = lay.gemm_end, lay.decay_end, lay.total
         # GEMM weights: decayed, bf16 shadow rewritten in the same pass
-        ops.adamw(p[:ge], g[:ge], self._m[:ge], self._v[:ge], shadow, ge, g0["lr"], b1, b2, g0["eps"], g0["weight_decay"], bc1, bc2, scale)
+        z = self.fused_zero_grad
+        ops.adamw(p[:ge], g[:ge], self._m[:ge], self._v[:ge], shadow, ge, g0["lr"], b1, b2, g0["eps"], g0["weight_decay"], bc1, bc2,
+                  scale, z)
         if de > ge:
             ops.adamw(p[ge:de], g[ge:de], self._m[ge:de], self._v[ge:de], None, de - ge, g0["lr"], b1, b2, g0["eps"],
-                      g0["weight_decay"], bc1, bc2, scale)
+                      g0["weight_decay"], bc1, bc2, scale, z)
         b1n, b2n = g1["betas"]
         ops.adamw(p[de:], g[de:], self._m[de:], self._v[de:], None, n - de, g1["lr"], b1n, b2n, g1["eps"], 0.0,
-                  1.0 - b1n ** t, 1.0 - b2n ** t, scale)
+                  1.0 - b1n ** t, 1.0 - b2n ** t, scale, z)
+        self._grads_clean = z
         model.mark_shadow_fresh()
         return loss
+
+    def zero_grad(self, set_to_none: bool = True):
+        if self._grads_clean:
+            self._grads_clean = False      # already zeroed by step(); keep .grad bound to the flat views
+            return
+        super().zero_grad(set_to_none=set_to_none)
 
     def grad_norm(self) -> torch.Tensor:
         """Global gradient norm of the last ``step`` (device scalar; only with max_grad_norm)."""

@@ -61,10 +61,12 @@ VITK_API int vitk_patchify_f32(const float* pixel_values, int64_t B, int64_t H, 
 VITK_API int vitk_layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps,
                        int64_t M, int64_t D, void* y_bf16, float* mean, float* rstd, vitk_stream_t stream);
 /* dx = dres + LNbwd(dy) (bf16 [M,D]; dres may be NULL); dgamma/dbeta fp32 [D] are ACCUMULATED
- * (+=) with atomics, so zero them first for a plain gradient. */
+ * (+=) with atomics, so zero them first for a plain gradient.  dxsum (optional, fp32 [D]) += Σ_rows dx:
+ * dx is also the output gradient of the Linear that fed this residual stream, so this is that layer's
+ * bias gradient (aten::sum in HF's AddmmBackward) without another pass over dx. */
 VITK_API int vitk_layernorm_bwd(const void* dy_bf16, const float* x, int64_t ldx, const float* mean, const float* rstd,
                        const float* gamma, const void* dres_bf16, int64_t M, int64_t D, void* dx_bf16,
-                       float* dgamma, float* dbeta, vitk_stream_t stream);
+                       float* dgamma, float* dbeta, float* dxsum, vitk_stream_t stream);
 
 /* ------------------------------------------------------------------ dense contraction
  * Replaces aten::addmm / aten::mm (+ fused bias/GELU/residual elementwise ops) for the patch
@@ -161,11 +163,12 @@ VITK_API int vitk_head_bwd(const float* h, const float* mean, const float* rstd,
  * torch.optim.AdamW semantics as HF Trainer configures it (trainer.py:1143-1217,1760):
  *   g' = g·(*grad_scale)   (grad_scale: device pointer, NULL = 1; see vitk_clip_scale)
  *   p ← p·(1 − lr·wd);  m ← m + (1−β1)(g' − m);  v ← v + (1−β2)(g'² − v);
- *   p ← p − lr/bias_corr1 · m / (√v/√bias_corr2 + eps);   p_bf16 ← bf16(p) when p_bf16 != NULL.
+ *   p ← p − lr/bias_corr1 · m / (√v/√bias_corr2 + eps);   p_bf16 ← bf16(p) when p_bf16 != NULL;
+ *   g ← 0 when zero_grad != 0 (optimizer.zero_grad() folded into the same pass).
  * n multiple of 4; all buffers 16-byte aligned. */
-VITK_API int vitk_adamw(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, float lr, float beta1,
+VITK_API int vitk_adamw(float* p, float* g, float* m, float* v, void* p_bf16, int64_t n, float lr, float beta1,
                float beta2, float eps, float weight_decay, float bias_corr1, float bias_corr2,
-               const float* grad_scale, vitk_stream_t stream);
+               const float* grad_scale, int zero_grad, vitk_stream_t stream);
 /* out[0] += Σ x²  (global gradient norm, trainer.py:2489-2493). */
 VITK_API int vitk_sumsq_f32(const float* x, int64_t n, float* out, vitk_stream_t stream);
 /* scale[0] = min(1, max_norm / (sqrt(sumsq[0]) + 1e-6))  (torch.nn.utils.clip_grad_norm_). */

@@ -54,8 +54,10 @@ def test_layernorm_fwd_bwd(ops, M, D):
     assert torch.allclose(rstd, torch.rsqrt(x.var(1, unbiased=False) + eps), rtol=1e-4)
     dgamma = torch.zeros(D, device=dev)
     dbeta = torch.zeros(D, device=dev)
-    dx = ops.layernorm_bwd(dy, x, mean, rstd, gamma, dres, dgamma, dbeta)
+    dxsum = torch.ones(D, device=dev)
+    dx = ops.layernorm_bwd(dy, x, mean, rstd, gamma, dres, dgamma, dbeta, dxsum=dxsum)
     ref_dx = xr.grad + dres.float()
+    assert torch.allclose(dxsum, 1 + dx.float().sum(0), rtol=1e-4, atol=1e-3 * max(1.0, M ** 0.5))
     assert (dx.float() - ref_dx).abs().max() <= 2 ** -7 * ref_dx.abs().max() + 1e-5
     assert torch.allclose(dgamma, gr.grad, rtol=2e-4, atol=2e-4 * gr.grad.abs().max().item())
     assert torch.allclose(dbeta, br.grad, rtol=2e-4, atol=2e-4 * br.grad.abs().max().item())
@@ -118,7 +120,9 @@ def test_cast_and_adamw(ops):
         grad = torch.randn(n, generator=g).to(dev)
         ref.grad = grad.clone()
         opt.step()
-        ops.adamw(p, grad, m, v, p16, n, 1e-3, 0.9, 0.999, 1e-8, 0.01, 1 - 0.9 ** t, 1 - 0.999 ** t)
+        gcopy = grad.clone()
+        ops.adamw(p, gcopy, m, v, p16, n, 1e-3, 0.9, 0.999, 1e-8, 0.01, 1 - 0.9 ** t, 1 - 0.999 ** t, zero_grad=(t == 2))
+        assert torch.equal(gcopy, torch.zeros_like(grad) if t == 2 else grad)
         assert torch.allclose(p, ref.detach(), atol=2e-6, rtol=1e-5)
         assert torch.equal(p16, p.to(torch.bfloat16))
     # global-norm clip scale
