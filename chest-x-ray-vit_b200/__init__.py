@@ -6,6 +6,7 @@ ViT-Training.py:83-132 drives.  Public surface:
   ops ................................... tensor-level wrappers over the C ABI (include/vitk.h)
   VitkAdamW ............................. flat-buffer AdamW + grad clip (optim.py)
   GradSync .............................. bucketed NCCL gradient all-reduce (parallel.py)
+  custom_ops ............................ torch.library custom ops + HF AttentionInterface plug-in
 """
 from . import _lib, ops  # noqa: F401
 
@@ -23,7 +24,7 @@ def __getattr__(name):
     if name == "GradSync":
         from .parallel import GradSync
         return GradSync
-    if name in ("modeling", "engine", "optim", "parallel"):
+    if name in ("modeling", "engine", "optim", "parallel", "custom_ops"):
         import importlib
         return importlib.import_module(f"{__name__}.{name}")
     raise AttributeError(name)
