@@ -168,3 +168,37 @@ def test_no_grad_and_custom_loss_on_logits():
         o1 = m(pixel_values=x8, labels=y)
         m(pixel_values=x8, labels=y)
         o1.loss.backward()
+
+
+def test_vit_large_16_384_matches_oracle():
+    """BASELINE.json configs[4] shape family (ViT-L/16@384: D=1024, H=16, F=4096, L=24), batch 1 on one GPU:
+    logits / loss and every gradient against the fp32 CPU oracle."""
+    cfg = O.VIT_L16_384
+    params = O.init_params(cfg, 0, 123)
+    g = torch.Generator().manual_seed(11)
+    x8, y = O.synth_inputs(cfg, 1, g)
+    m = _model(cfg, params)
+    out = m(pixel_values=x8[:, 0].cuda(), labels=y.cuda())
+    out.loss.backward()
+    torch.cuda.synchronize()
+    torch.set_num_threads(os.cpu_count() or 1)
+    loss_ref, logits_ref, ref = O.forward_backward(params, cfg, O.normalize_gray(x8), y)
+    dl = (out.logits.cpu() - logits_ref).abs().max().item()
+    rl = abs(out.loss.item() - loss_ref.item()) / abs(loss_ref.item())
+    worst = _check_grads(m, ref)
+    print(f"vit-L b1: logits max-abs {dl:.3e}, loss rel {rl:.3e}, worst grad cosine {worst[0]:.6f} ({worst[1]})")
+    assert dl <= LOGIT_TOL and rl <= LOSS_RTOL
+
+
+def test_vitb16_224_batch_sweep_is_batch_invariant():
+    """BASELINE.json configs[3]: inference at 224 px; logits of an image must not depend on the batch it is in."""
+    cfg = O.VIT_B16_224
+    m = _model(cfg, O.init_params(cfg, 0, 123)).eval()
+    g = torch.Generator().manual_seed(5)
+    x8 = torch.randint(0, 256, (64, 224, 224), dtype=torch.uint8, generator=g).cuda()
+    with torch.no_grad():
+        big = m(pixel_values=x8).logits
+        for bs in (1, 2, 7, 32):
+            part = m(pixel_values=x8[:bs]).logits
+            assert (part - big[:bs]).abs().max() < 5e-3, bs
+    assert torch.isfinite(big).all()
