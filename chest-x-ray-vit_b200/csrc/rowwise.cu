@@ -133,77 +133,114 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
   }
 }
 
-// dx = dres + r·(g − mean(g) − x̂·mean(g·x̂)), g = dy·γ.  Each warp walks rows with a grid stride and
-// keeps its dγ/dβ partials in registers; one smem reduction + one atomicAdd per column per block.
+// dx = dres + r·(g − mean(g) − x̂·mean(g·x̂)), g = dy·γ.  A PAIR of warps owns a row (each warp half of the
+// columns; the two row sums are exchanged through shared memory with a 64-thread named barrier), so a thread
+// keeps only half of the dγ / dβ / Σdx partials and of the row in registers: ~60 registers instead of 174,
+// 4× the resident warps of the one-warp-per-row version, which is what an HBM-bound kernel needs.  Pairs walk
+// rows with a grid stride; one smem reduction + one atomicAdd per column per block at the end.
+// rs: logical row r lives at physical row r·rs of dy / dres / dx / mean / rstd (x has its own ldx); rs = T walks
+// only the CLS rows of a [B,T,D] tensor.
 template <int VPL>
-__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x,
-                                                            long long ldx, const float* __restrict__ mean,
-                                                            const float* __restrict__ rstd, const float* __restrict__ gamma,
-                                                            const __nv_bfloat16* __restrict__ dres, int M,
-                                                            __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma,
-                                                            float* __restrict__ dbeta, float* __restrict__ dxsum) {
+__global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x,
+                                                               long long ldx, const float* __restrict__ mean,
+                                                               const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                               const __nv_bfloat16* __restrict__ dres, int M, long long rs,
+                                                               __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma,
+                                                               float* __restrict__ dbeta, float* __restrict__ dxsum) {
   constexpr int D = VPL * 128;
+  constexpr int kSplit = (VPL % 2 == 0) ? 2 : 1;   // warps per row
+  constexpr int V = VPL / kSplit;                   // float4 chunks per lane
   pdl_wait();
   pdl_launch_dependents();
-  extern __shared__ float red[];  // [warps][D] reused for dγ, dβ and Σdx
+  extern __shared__ float red[];                    // [row slots][D] reused for dγ, dβ and Σdx
+  __shared__ float2 xch[2][8];                      // [row parity][warp]: partial (Σg, Σg·x̂) of each warp
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  float4 gam[VPL], dg[VPL], db[VPL], dsx[VPL];
+  const int slot = warp / kSplit, half = warp % kSplit, nslots = nwarps / kSplit;
+  const int c0 = half * V * 32 + lane;              // this lane's float4 chunks: c0 + 32·i
+  const float4* gam4 = reinterpret_cast<const float4*>(gamma);
+  float4 dg[V], db[V], dsx[V];
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    gam[i] = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * i);
+  for (int i = 0; i < V; ++i) {
     dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     dsx[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  for (int row = blockIdx.x * nwarps + warp; row < M; row += gridDim.x * nwarps) {
-    const float mu = __ldg(mean + row), r = __ldg(rstd + row);
-    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long long>(row) * ldx);
-    const uint2* dyr = reinterpret_cast<const uint2*>(dy + static_cast<long long>(row) * D);
-    float4 xh[VPL], g[VPL];
+  // software pipeline: the next row's x / dy / dres are in flight while this row is reduced and written
+  const int row_step = gridDim.x * nslots;
+  int row = blockIdx.x * nslots + slot;
+  float4 xn[V];
+  uint2 dn[V], rn[V];
+  auto fetch = [&](int rw) {
+    const long long pr = static_cast<long long>(rw) * rs;
+    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long long>(rw) * ldx);
+    const uint2* dyr = reinterpret_cast<const uint2*>(dy + pr * D);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      xn[i] = __ldg(xr + c0 + 32 * i);
+      dn[i] = __ldg(dyr + c0 + 32 * i);
+      rn[i] = dres ? __ldg(reinterpret_cast<const uint2*>(dres + pr * D) + c0 + 32 * i) : make_uint2(0u, 0u);
+    }
+  };
+  if (row < M) fetch(row);
+  int parity = 0;
+  for (; row < M; row += row_step, parity ^= 1) {
+    const long long prow = static_cast<long long>(row) * rs;
+    const float mu = __ldg(mean + prow), r = __ldg(rstd + prow);
+    float4 xv[V];
+    uint2 dw[V], rw_[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) { xv[i] = xn[i]; dw[i] = dn[i]; rw_[i] = rn[i]; }
+    if (row + row_step < M) fetch(row + row_step);
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      const float4 xv = __ldg(xr + lane + 32 * i);
-      const uint2 dw = __ldg(dyr + lane + 32 * i);
-      const float2 d01 = unbf2(dw.x), d23 = unbf2(dw.y);
-      xh[i] = make_float4((xv.x - mu) * r, (xv.y - mu) * r, (xv.z - mu) * r, (xv.w - mu) * r);
-      g[i] = make_float4(d01.x * gam[i].x, d01.y * gam[i].y, d23.x * gam[i].z, d23.y * gam[i].w);
-      s1 += (g[i].x + g[i].y) + (g[i].z + g[i].w);
-      s2 += (g[i].x * xh[i].x + g[i].y * xh[i].y) + (g[i].z * xh[i].z + g[i].w * xh[i].w);
-      dg[i].x += d01.x * xh[i].x; dg[i].y += d01.y * xh[i].y; dg[i].z += d23.x * xh[i].z; dg[i].w += d23.y * xh[i].w;
+    for (int i = 0; i < V; ++i) {
+      const float4 gm = __ldg(gam4 + c0 + 32 * i);
+      const float2 d01 = unbf2(dw[i].x), d23 = unbf2(dw[i].y);
+      const float h0 = (xv[i].x - mu) * r, h1 = (xv[i].y - mu) * r, h2 = (xv[i].z - mu) * r, h3 = (xv[i].w - mu) * r;
+      const float g0 = d01.x * gm.x, g1 = d01.y * gm.y, g2 = d23.x * gm.z, g3 = d23.y * gm.w;
+      s1 += (g0 + g1) + (g2 + g3);
+      s2 += (g0 * h0 + g1 * h1) + (g2 * h2 + g3 * h3);
+      dg[i].x += d01.x * h0; dg[i].y += d01.y * h1; dg[i].z += d23.x * h2; dg[i].w += d23.y * h3;
       db[i].x += d01.x; db[i].y += d01.y; db[i].z += d23.x; db[i].w += d23.y;
     }
-    const float m1 = warp_sum(s1) * (1.0f / D), m2 = warp_sum(s2) * (1.0f / D);
-    uint2* dxr = reinterpret_cast<uint2*>(dx + static_cast<long long>(row) * D);
-    const uint2* rr = dres ? reinterpret_cast<const uint2*>(dres + static_cast<long long>(row) * D) : nullptr;
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (kSplit == 2) {   // both warps of the pair take the same trip count, so the named barrier is always matched
+      if (lane == 0) xch[parity][warp] = make_float2(s1, s2);
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + slot) : "memory");
+      const float2 o = xch[parity][warp ^ 1];
+      s1 += o.x;
+      s2 += o.y;
+    }
+    const float m1 = s1 * (1.0f / D), m2 = s2 * (1.0f / D);
+    uint2* dxr = reinterpret_cast<uint2*>(dx + prow * D);
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      float o0 = r * (g[i].x - m1 - xh[i].x * m2), o1 = r * (g[i].y - m1 - xh[i].y * m2);
-      float o2 = r * (g[i].z - m1 - xh[i].z * m2), o3 = r * (g[i].w - m1 - xh[i].w * m2);
-      if (rr) {
-        const uint2 w = __ldg(rr + lane + 32 * i);
-        const float2 a = unbf2(w.x), b = unbf2(w.y);
-        o0 += a.x; o1 += a.y; o2 += b.x; o3 += b.y;
-      }
+    for (int i = 0; i < V; ++i) {
+      const float4 gm = __ldg(gam4 + c0 + 32 * i);
+      const float2 d01 = unbf2(dw[i].x), d23 = unbf2(dw[i].y);
+      const float h0 = (xv[i].x - mu) * r, h1 = (xv[i].y - mu) * r, h2 = (xv[i].z - mu) * r, h3 = (xv[i].w - mu) * r;
+      const float2 a = unbf2(rw_[i].x), b = unbf2(rw_[i].y);
+      const float o0 = r * (d01.x * gm.x - m1 - h0 * m2) + a.x, o1 = r * (d01.y * gm.y - m1 - h1 * m2) + a.y;
+      const float o2 = r * (d23.x * gm.z - m1 - h2 * m2) + b.x, o3 = r * (d23.y * gm.w - m1 - h3 * m2) + b.y;
       const uint2 packed = make_uint2(bf2(o0, o1), bf2(o2, o3));
-      dxr[lane + 32 * i] = packed;
+      dxr[c0 + 32 * i] = packed;
       if (dxsum != nullptr) {   // column sums of the bf16 values actually stored (what the wgrad GEMM will read)
         const float2 s01 = unbf2(packed.x), s23 = unbf2(packed.y);
         dsx[i].x += s01.x; dsx[i].y += s01.y; dsx[i].z += s23.x; dsx[i].w += s23.y;
       }
     }
   }
-  // block reduction of the per-warp partials
+  // block reduction of the per-slot partials
   float4* red4 = reinterpret_cast<float4*>(red);
   const int npass = dxsum != nullptr ? 3 : 2;
   for (int pass = 0; pass < npass; ++pass) {
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) red4[warp * (D / 4) + lane + 32 * i] = pass == 0 ? dg[i] : (pass == 1 ? db[i] : dsx[i]);
+    for (int i = 0; i < V; ++i) red4[slot * (D / 4) + c0 + 32 * i] = pass == 0 ? dg[i] : (pass == 1 ? db[i] : dsx[i]);
     __syncthreads();
     float* dst = pass == 0 ? dgamma : (pass == 1 ? dbeta : dxsum);
     for (int c = threadIdx.x; c < D; c += blockDim.x) {
       float s = 0.f;
-      for (int w = 0; w < nwarps; ++w) s += red[w * D + c];
+      for (int w = 0; w < nslots; ++w) s += red[w * D + c];
       atomicAdd(dst + c, s);
     }
     __syncthreads();
@@ -292,14 +329,15 @@ static int ln_fwd_launch(const float* x, long long ldx, const float* gamma, cons
 }
 template <int VPL>
 static int ln_bwd_launch(const __nv_bfloat16* dy, const float* x, long long ldx, const float* mean, const float* rstd,
-                         const float* gamma, const __nv_bfloat16* dres, int M, __nv_bfloat16* dx, float* dgamma,
+                         const float* gamma, const __nv_bfloat16* dres, int M, long long rs, __nv_bfloat16* dx, float* dgamma,
                          float* dbeta, float* dxsum, cudaStream_t s) {
   const int warps = 8;
-  int grid = num_sms() * 3;
-  const int need = (M + warps - 1) / warps;
+  const int slots = (VPL % 2 == 0) ? warps / 2 : warps;      // rows in flight per block (a warp pair per row)
+  int grid = num_sms() * 2;
+  const int need = (M + slots - 1) / slots;
   if (grid > need) grid = need;
-  const size_t smem = static_cast<size_t>(warps) * VPL * 128 * sizeof(float);
-  VITK_CUDA(launch_pdl(layernorm_bwd_kernel<VPL>, dim3(grid), dim3(warps * 32), smem, s, dy, x, ldx, mean, rstd, gamma, dres, M, dx,
+  const size_t smem = static_cast<size_t>(slots) * VPL * 128 * sizeof(float);
+  VITK_CUDA(launch_pdl(layernorm_bwd_kernel<VPL>, dim3(grid), dim3(warps * 32), smem, s, dy, x, ldx, mean, rstd, gamma, dres, M, rs, dx,
                        dgamma, dbeta, dxsum));
   VITK_LAUNCH_CHECK("layernorm_bwd_kernel");
   return 0;
@@ -362,7 +400,15 @@ extern "C" VITK_API int vitk_layernorm_fwd(const float* x, int64_t ldx, const fl
 extern "C" VITK_API int vitk_layernorm_bwd(const void* dy, const float* x, int64_t ldx, const float* mean, const float* rstd,
                                   const float* gamma, const void* dres, int64_t M, int64_t D, void* dx, float* dgamma,
                                   float* dbeta, float* dxsum, vitk_stream_t stream) {
+  return vitk_layernorm_bwd_rows(dy, x, ldx, mean, rstd, gamma, dres, M, D, 1, dx, dgamma, dbeta, dxsum, stream);
+}
+
+extern "C" VITK_API int vitk_layernorm_bwd_rows(const void* dy, const float* x, int64_t ldx, const float* mean, const float* rstd,
+                                       const float* gamma, const void* dres, int64_t M, int64_t D, int64_t row_stride,
+                                       void* dx, float* dgamma, float* dbeta, float* dxsum, vitk_stream_t stream) {
   VITK_REQUIRE(dy && x && mean && rstd && gamma && dx && dgamma && dbeta, VITK_EINVAL, "layernorm_bwd: NULL argument");
+  VITK_REQUIRE(row_stride >= 1, VITK_EINVAL, "layernorm_bwd: row_stride must be >= 1");
+  const long long rs = row_stride;
   VITK_REQUIRE(M > 0 && M < (1ll << 31), VITK_EINVAL, "layernorm_bwd: bad M");
   VITK_REQUIRE(ldx >= D && ldx % 4 == 0 && aligned16(x) && aligned16(dy) && aligned16(dx) && aligned16(gamma) &&
                    (dres == nullptr || aligned16(dres)),
@@ -372,11 +418,11 @@ extern "C" VITK_API int vitk_layernorm_bwd(const void* dy, const float* x, int64
   const __nv_bfloat16* rr = static_cast<const __nv_bfloat16*>(dres);
   __nv_bfloat16* dxx = static_cast<__nv_bfloat16*>(dx);
   switch (D) {
-    case 128: return ln_bwd_launch<1>(dyy, x, ldx, mean, rstd, gamma, rr, (int)M, dxx, dgamma, dbeta, dxsum, s);
-    case 256: return ln_bwd_launch<2>(dyy, x, ldx, mean, rstd, gamma, rr, (int)M, dxx, dgamma, dbeta, dxsum, s);
-    case 512: return ln_bwd_launch<4>(dyy, x, ldx, mean, rstd, gamma, rr, (int)M, dxx, dgamma, dbeta, dxsum, s);
-    case 768: return ln_bwd_launch<6>(dyy, x, ldx, mean, rstd, gamma, rr, (int)M, dxx, dgamma, dbeta, dxsum, s);
-    case 1024: return ln_bwd_launch<8>(dyy, x, ldx, mean, rstd, gamma, rr, (int)M, dxx, dgamma, dbeta, dxsum, s);
+    case 128: return ln_bwd_launch<1>(dyy, x, ldx, mean, rstd, gamma, rr, (int)M, rs, dxx, dgamma, dbeta, dxsum, s);
+    case 256: return ln_bwd_launch<2>(dyy, x, ldx, mean, rstd, gamma, rr, (int)M, rs, dxx, dgamma, dbeta, dxsum, s);
+    case 512: return ln_bwd_launch<4>(dyy, x, ldx, mean, rstd, gamma, rr, (int)M, rs, dxx, dgamma, dbeta, dxsum, s);
+    case 768: return ln_bwd_launch<6>(dyy, x, ldx, mean, rstd, gamma, rr, (int)M, rs, dxx, dgamma, dbeta, dxsum, s);
+    case 1024: return ln_bwd_launch<8>(dyy, x, ldx, mean, rstd, gamma, rr, (int)M, rs, dxx, dgamma, dbeta, dxsum, s);
     default: return set_error(VITK_EINVAL, "layernorm_bwd: hidden size %lld unsupported", (long long)D);
   }
 }

@@ -170,20 +170,47 @@ class Arena:
             return _gemm(*a, max_ctas=mc, **k)
         pl.gemm = gemm_capped
         dh, dh1 = self.dh
-        pl.add("vitk_fill_zero", _p(dh), dh.numel() * 2)
         pl.add("vitk_head_bwd", _p(self.h_last), _p(self.hstat[0]), _p(self.hstat[1]), _p(w["gf"]), _p(w["bf"]), _p(w["wc"]),
                B, T, D, Cn, _p(self.dlogits if from_loss else self.dlogits_in), _p(self.dloss) if from_loss else None,
                _p(dh), _p(g["wc"]), _p(g["bc"]), _p(g["gf"]), _p(g["bf"]))
-        # Bias gradients of the two D-wide linears (fc2, out-proj) are column sums of the residual-stream gradients
-        # that the LayerNorm backward kernels produce anyway, so those kernels emit them (dxsum): dh entering layer
-        # l is the dx of layer l+1's LN1 backward (→ fc2 bias of layer l), dh1 is the dx of layer l's LN2 backward
-        # (→ out-proj bias of layer l).  Only the top layer's fc2 bias needs a separate pass (its dh comes from the head).
-        for l in reversed(range(L)):
+        # ---- top layer: only the B CLS rows of the residual stream carry gradient (HF modeling_vit.py:641 reads
+        # sequence_output[:, 0]), so its MLP and attention-output backward run on strided [B, ·] views of the same
+        # buffers (row stride T·width) instead of all M rows.  The zero rows are materialised only where the dense
+        # attention backward needs them (dO) and in the residual gradient that flows on (dh1).
+        # Algorithmic FLOPs are still counted dense in bench.py; this removes work, it does not approximate.
+        def cls_rows(t: torch.Tensor) -> torch.Tensor:
+            width = t.shape[1]
+            return t.view(B, T * width)[:, :width]
+
+        l = L - 1
+        lw, lg, st = w["layers"][l], g["layers"][l], self.st[l]
+        dh_c, dh1_c, dn_c, do_c = cls_rows(dh), cls_rows(dh1), cls_rows(self.dn), cls_rows(self.do)
+        du_c, a_c, gp_c, n2_c, o_c = cls_rows(self.du), cls_rows(self.a[l]), cls_rows(self.gp[l]), cls_rows(self.n2[l]), cls_rows(self.o[l])
+        pl.gemm(dh_c, a_c, D, Fi, B, lg["w2"], EPI_ACCUM_F32, a_mn=True, b_mn=True)
+        pl.add("vitk_colsum_bf16", _p(dh_c), B, D, T * D, _p(lg["bf2"]))
+        pl.gemm(dh_c, lw["w2_16"], B, Fi, D, du_c, EPI_MUL_BF16, b_mn=True, aux=gp_c)
+        pl.gemm(du_c, n2_c, Fi, D, B, lg["w1"], EPI_ACCUM_F32, a_mn=True, b_mn=True)
+        pl.add("vitk_colsum_bf16", _p(du_c), B, Fi, T * Fi, _p(lg["bf1"]))
+        pl.gemm(du_c, lw["w1_16"], B, D, Fi, dn_c, EPI_STORE_BF16, b_mn=True)
+        pl.add("vitk_fill_zero", _p(dh1), dh1.numel() * 2)
+        pl.add("vitk_layernorm_bwd_rows", _p(self.dn), _p(self.h1[l]), T * D, _p(st[2]), _p(st[3]), _p(lw["g2"]), _p(dh), B, D, T,
+               _p(dh1), _p(lg["g2"]), _p(lg["b2"]), _p(lg["bo"]))
+        pl.gemm(dh1_c, o_c, D, D, B, lg["wo"], EPI_ACCUM_F32, a_mn=True, b_mn=True)
+        pl.add("vitk_fill_zero", _p(self.do), self.do.numel() * 2)
+        pl.gemm(dh1_c, lw["wo16"], B, D, D, do_c, EPI_STORE_BF16, b_mn=True)
+        pl.add("vitk_attn_bwd", _p(self.qkv[l]), _p(self.o[l]), _p(self.do), _p(self.lse[l]), B, T, H, scale,
+               _p(self.dqkv), _p(self.attn_ws))
+        pl.gemm(self.dqkv, self.n1[l], 3 * D, D, M, lg["wqkv"], EPI_ACCUM_F32, a_mn=True, b_mn=True)
+        pl.add("vitk_colsum_bf16", _p(self.dqkv), M, 3 * D, 3 * D, _p(lg["bqkv"]))
+        pl.gemm(self.dqkv, lw["wqkv16"], M, D, 3 * D, self.dn, EPI_STORE_BF16, b_mn=True)
+        pl.add("vitk_layernorm_bwd", _p(self.dn), _p(self.h[l]), D, _p(st[0]), _p(st[1]), _p(lw["g1"]), _p(dh1), M, D,
+               _p(dh), _p(lg["g1"]), _p(lg["b1"]), _p(g["layers"][l - 1]["bf2"]) if l > 0 else None)
+        pl.call(lambda l=l: eng._layer_grads_ready(l))
+        # ---- layers L-2 … 0: dense
+        for l in reversed(range(L - 1)):
             lw, lg, st = w["layers"][l], g["layers"][l], self.st[l]
             # MLP
             pl.gemm(dh, self.a[l], D, Fi, M, lg["w2"], EPI_ACCUM_F32, a_mn=True, b_mn=True)
-            if l == L - 1:
-                pl.add("vitk_colsum_bf16", _p(dh), M, D, D, _p(lg["bf2"]))
             pl.gemm(dh, lw["w2_16"], M, Fi, D, self.du, EPI_MUL_BF16, b_mn=True, aux=self.gp[l])
             pl.gemm(self.du, self.n2[l], Fi, D, M, lg["w1"], EPI_ACCUM_F32, a_mn=True, b_mn=True)
             pl.add("vitk_colsum_bf16", _p(self.du), M, Fi, Fi, _p(lg["bf1"]))

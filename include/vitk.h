@@ -67,6 +67,12 @@ VITK_API int vitk_layernorm_fwd(const float* x, int64_t ldx, const float* gamma,
 VITK_API int vitk_layernorm_bwd(const void* dy_bf16, const float* x, int64_t ldx, const float* mean, const float* rstd,
                        const float* gamma, const void* dres_bf16, int64_t M, int64_t D, void* dx_bf16,
                        float* dgamma, float* dbeta, float* dxsum, vitk_stream_t stream);
+/* Same over a strided subset of rows: logical row r is physical row r·row_stride of dy / dres / dx / mean / rstd
+ * (x uses ldx).  With row_stride = T and ldx = T·D it touches only the B CLS rows of [B,T,D] tensors — all that
+ * carries gradient in the top encoder layer (HF modeling_vit.py:641 selects sequence_output[:, 0]). */
+VITK_API int vitk_layernorm_bwd_rows(const void* dy_bf16, const float* x, int64_t ldx, const float* mean, const float* rstd,
+                       const float* gamma, const void* dres_bf16, int64_t M, int64_t D, int64_t row_stride,
+                       void* dx_bf16, float* dgamma, float* dbeta, float* dxsum, vitk_stream_t stream);
 
 /* ------------------------------------------------------------------ dense contraction
  * Replaces aten::addmm / aten::mm (+ fused bias/GELU/residual elementwise ops) for the patch
