@@ -220,8 +220,9 @@ def instrumented_gemm_time(ar, plans, stream):
         fl = gemm_flops_of_plan(plan)
         for (fn, a, name), f in zip(plan.steps, fl):
             if fn is None:
-                a[0]()
-                continue
+                if name == "python":
+                    a[0]()
+                continue           # fork / join markers: this replay is single-stream
             if f is not None:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()

@@ -34,9 +34,24 @@ class _Plan:
     def __init__(self):
         self.steps: List[Tuple[object, tuple, str]] = []
         self.gemm_flops: Dict[int, float] = {}      # step index → 2·M·N·K (bench.py's roofline leg)
+        self.side_steps = set()                     # indices of steps launched on the side stream
         self._keep = []      # keeps GemmArgs structs alive
+        self._side = False
+
+    def side(self, on: bool):
+        """Steps added while on=True are launched on the engine's side stream (weight-gradient work that only the
+        optimizer consumes); fork()/join() order it against the main chain."""
+        self._side = on
+
+    def fork(self):
+        self.steps.append((None, (), "fork"))        # side stream waits for everything enqueued on main so far
+
+    def join(self):
+        self.steps.append((None, (), "join"))        # main stream waits for everything enqueued on side so far
 
     def add(self, name: str, *args):
+        if self._side:
+            self.side_steps.add(len(self.steps))
         self.steps.append((getattr(_lib.lib(), name), args, name))
 
     def gemm(self, a, b, M, N, K, d, epilogue, a_mn=False, b_mn=False, d2=None, bias=None, aux=None, rows_in=0,
@@ -53,17 +68,30 @@ class _Plan:
         g.rows_in, g.rows_out, g.row_off, g.tile_n, g.max_ctas, g.variant = rows_in, rows_out, row_off, tile_n, max_ctas, variant
         self._keep.append(g)
         self.gemm_flops[len(self.steps)] = 2.0 * M * N * K
+        if self._side:
+            self.side_steps.add(len(self.steps))
         self.steps.append((_lib.lib().vitk_gemm_bf16, (C.byref(g),), "vitk_gemm_bf16"))
 
     def call(self, fn: Callable[[], None]):
         self.steps.append((None, (fn,), "python"))
 
-    def run(self, stream: int):
-        for fn, args, name in self.steps:
+    def run(self, stream: int, side_stream: Optional[torch.cuda.Stream] = None):
+        side = side_stream.cuda_stream if side_stream is not None else stream
+        for i, (fn, args, name) in enumerate(self.steps):
             if fn is None:
-                args[0]()
+                if name == "python":
+                    args[0]()
+                elif side_stream is not None:
+                    main = torch.cuda.current_stream()
+                    ev = torch.cuda.Event()
+                    if name == "fork":
+                        ev.record(main)
+                        side_stream.wait_event(ev)
+                    else:
+                        ev.record(side_stream)
+                        main.wait_event(ev)
                 continue
-            rc = fn(*args, stream)
+            rc = fn(*args, side if i in self.side_steps else stream)
             if rc != 0:
                 _lib.check(rc, name)
 
@@ -207,24 +235,41 @@ class Arena:
                _p(dh), _p(lg["g1"]), _p(lg["b1"]), _p(g["layers"][l - 1]["bf2"]) if l > 0 else None)
         pl.call(lambda l=l: eng._layer_grads_ready(l))
         # ---- layers L-2 … 0: dense
+        # Dense layers.  Weight gradients (and the two wide bias column sums) are consumed only by the optimizer, so
+        # they go to a side stream: fork after the tensor they read is produced, join once per layer before the
+        # buffers they read are overwritten.  Their CTAs fill the SMs the main chain leaves idle in its partial last
+        # waves and kernel tails (every kernel here is a persistent grid sized for the whole GPU).
         for l in reversed(range(L - 1)):
             lw, lg, st = w["layers"][l], g["layers"][l], self.st[l]
             # MLP
+            pl.fork()
+            pl.side(True)
             pl.gemm(dh, self.a[l], D, Fi, M, lg["w2"], EPI_ACCUM_F32, a_mn=True, b_mn=True)
+            pl.side(False)
             pl.gemm(dh, lw["w2_16"], M, Fi, D, self.du, EPI_MUL_BF16, b_mn=True, aux=self.gp[l])
+            pl.fork()
+            pl.side(True)
             pl.gemm(self.du, self.n2[l], Fi, D, M, lg["w1"], EPI_ACCUM_F32, a_mn=True, b_mn=True)
             pl.add("vitk_colsum_bf16", _p(self.du), M, Fi, Fi, _p(lg["bf1"]))
+            pl.side(False)
             pl.gemm(self.du, lw["w1_16"], M, D, Fi, self.dn, EPI_STORE_BF16, b_mn=True)
             pl.add("vitk_layernorm_bwd", _p(self.dn), _p(self.h1[l]), D, _p(st[2]), _p(st[3]), _p(lw["g2"]), _p(dh), M, D,
                    _p(dh1), _p(lg["g2"]), _p(lg["b2"]), _p(lg["bo"]))
             # attention
+            pl.fork()
+            pl.side(True)
             pl.gemm(dh1, self.o[l], D, D, M, lg["wo"], EPI_ACCUM_F32, a_mn=True, b_mn=True)
+            pl.side(False)
             pl.gemm(dh1, lw["wo16"], M, D, D, self.do, EPI_STORE_BF16, b_mn=True)
             pl.add("vitk_attn_bwd", _p(self.qkv[l]), _p(self.o[l]), _p(self.do), _p(self.lse[l]), B, T, H, scale,
                    _p(self.dqkv), _p(self.attn_ws))
+            pl.fork()
+            pl.side(True)
             pl.gemm(self.dqkv, self.n1[l], 3 * D, D, M, lg["wqkv"], EPI_ACCUM_F32, a_mn=True, b_mn=True)
             pl.add("vitk_colsum_bf16", _p(self.dqkv), M, 3 * D, 3 * D, _p(lg["bqkv"]))
+            pl.side(False)
             pl.gemm(self.dqkv, lw["wqkv16"], M, D, 3 * D, self.dn, EPI_STORE_BF16, b_mn=True)
+            pl.join()          # side work of this layer read dh / du / dh1 / dqkv, which the next kernels overwrite
             pl.add("vitk_layernorm_bwd", _p(self.dn), _p(self.h[l]), D, _p(st[0]), _p(st[1]), _p(lw["g1"]), _p(dh1), M, D,
                    _p(dh), _p(lg["g1"]), _p(lg["b1"]), _p(g["layers"][l - 1]["bf2"]) if l > 0 else None)
             pl.call(lambda l=l: eng._layer_grads_ready(l))
@@ -242,6 +287,8 @@ class Engine:
         self.ticket = 0
         self.arenas: Dict[Tuple[int, bool], Arena] = {}
         self.grad_sync = None            # parallel.GradSync, set by the caller for N>1
+        import os
+        self.side_stream = torch.cuda.Stream(device=self.dev) if os.environ.get("VITK_SIDE_STREAM", "1") != "0" else None
         self.w = self._weight_views(model.flat_parameters(), model.shadow())
         self.g = self._weight_views(model.flat_grads(), None)
         self._grad_views = {n: model.layout.view(model.flat_grads(), n) for n in model.layout.names}
@@ -363,13 +410,13 @@ class Engine:
         stream = torch.cuda.current_stream().cuda_stream
         if dloss is not None and dlogits is None:
             ar.dloss.copy_(dloss.reshape(1), non_blocking=True)
-            ar.bwd_loss.run(stream)
+            ar.bwd_loss.run(stream, self.side_stream)
         else:
             if dloss is not None:      # both the loss and the logits were used downstream
                 torch.add(dlogits.to(f32), ar.dlogits * dloss.to(f32), out=ar.dlogits_in)
             else:
                 ar.dlogits_in.copy_(dlogits)
-            ar.bwd_logits.run(stream)
+            ar.bwd_logits.run(stream, self.side_stream)
         ar.ticket = -1
 
     def _layer_grads_ready(self, l: int) -> None:
