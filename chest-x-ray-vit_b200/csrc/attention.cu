@@ -26,7 +26,7 @@
 namespace vitk {
 
 // Optional per-phase timeline (vitk_debug_timeline): CTA (0,0,0) records clock64() stamps.
-static long long* g_timeline = nullptr;
+long long* g_timeline = nullptr;   // also stamped by the CTA-pair GEMM (gemm2.cu)
 #define VITK_STAMP(slot)                                             \
   do {                                                               \
     if (tl != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0) tl[(slot)] = clock64(); \

@@ -36,7 +36,11 @@ constexpr int k2EpiWarps = 8;
 constexpr int k2FirstEpiWarp = 2;
 constexpr int k2Threads = (k2FirstEpiWarp + k2EpiWarps) * 32;   // 384
 constexpr int k2ABytes = k2BM * k2BK * 2;                       // 16 KB
-constexpr int k2SlabBytes = 4096;                               // per epilogue warp: 2 slabs of [32 rows × 64 B]
+#ifndef VITK_G2_SLABS
+#define VITK_G2_SLABS 2      // 2 and 4 measured equal (the epilogue is not waiting on its TMA stores)
+#endif
+constexpr int k2Slabs = VITK_G2_SLABS;                          // [32 rows × 64 B] slabs per epilogue warp (TMA stores in flight)
+constexpr int k2SlabBytes = k2Slabs * 2048;
 constexpr int k2StagingBytes = k2EpiWarps * k2SlabBytes;        // 32 KB
 constexpr int k2BiasBytes = 2 * 2 * 128 * 4;                     // bias slice (≤128 floats) per column half × tile parity
 constexpr int k2BarBytes = 256;
@@ -49,7 +53,10 @@ struct Cfg2 {
   // Operand bytes in flight are what hides the ≈3,200-cycle refill round trip (MMA retire → commit →
   // producer wake → TMA → L2 → complete_tx on the leader → MMA wake): measured k-block cadence ≈
   // (512 + 3200) / stages cycles, so every stage that fits in the 227 KB is used.
-  static constexpr int kStages = (BN == 256) ? 6 : (BN == 192 ? 6 : 8);   // 192 / 168 / 192 KB of operands in flight
+#ifndef VITK_G2_STAGES
+#define VITK_G2_STAGES 6     // 4, 5 and 6 measured equal: the K-block cadence is a throughput limit, not a latency one
+#endif
+  static constexpr int kStages = (BN == 256) ? VITK_G2_STAGES : (BN == 192 ? VITK_G2_STAGES : VITK_G2_STAGES + 2);
   static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;
   static constexpr int kSmemBytes = kStages * kStageBytes + k2StagingBytes + k2BiasBytes + k2BarBytes;   // no slack: smem_raw is declared 1024-aligned
 };
@@ -60,11 +67,16 @@ struct Gemm2Params {
   int epi;
   int has_d2;
   int dbg;            // VITK_GEMM_DBG experiment bits (0 in production): 1 skip stores, 2 skip aux, 4 skip TMEM loads,
-                      // 8 every CTA loads tile (0,0) (operands always L2-resident), 16 no MMAs (load pipeline only)
+                      // 8 every CTA loads tile (0,0) (operands always L2-resident), 16 no MMAs (load pipeline only),
+                      // 32 no TMA loads after the first ring fill (MMA pipeline only)
   const void* aux;
   long long ld_aux;
   const float* bias;
+  long long* tl;      // vitk_debug_timeline buffer (nullptr in production): the leader CTA of pair 0 stamps clock64() per
+                      // K block [4i]: producer passed the stage-empty wait, [4i+1]: MMA warp passed the stage-full wait,
+                      // [4i+2]: MMAs + commit issued; per tile [4096+4t]: epilogue warp 2 passed acc_full, [+1]: tile drained
 };
+extern long long* g_timeline;
 
 struct Work2 {
   int m_blk, n_blk, kb_begin, kb_end;
@@ -158,6 +170,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   const bool leader = cta_rank == 0;
   const int pair_id = blockIdx.x >> 1;
   const int num_pairs = gridDim.x >> 1;
+  const bool stamp = p.tl != nullptr && blockIdx.x == 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
@@ -192,6 +205,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     const uint32_t full0_leader = smem_u32(&full_bar[0]) & 0xFEFFFFFFu;
     int stage = 0;
     uint32_t phase = 0;
+    int kbi = 0;
     for (int w = pair_id; w < p.total_work; w += num_pairs) {
       const Work2 it = decode_work2(p, w);
       const int m0 = (p.dbg & 8) ? 0 : it.m_blk * (2 * k2BM) + static_cast<int>(cta_rank) * k2BM;
@@ -199,11 +213,15 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       const int kb_begin = it.kb_begin, kb_end = it.kb_end;
       for (int kb = kb_begin; kb < kb_end; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (stamp && L && kbi < 1024) p.tl[4 * kbi] = clock64();
+        ++kbi;
         uint8_t* sa = smem + stage * Cfg::kStageBytes;
         uint8_t* sb = sa + k2ABytes;
         const uint32_t bar = full0_leader + stage * 8;
         const int k0 = (p.dbg & 8) ? (kb & 7) * k2BK : kb * k2BK;
-        if (L) {
+        if ((p.dbg & 32) && kbi > kStages) {       // experiment: MMAs re-read stale stages, no TMA traffic at all
+          if (L && leader) mbar_arrive(&full_bar[stage]);
+        } else if (elect_one()) {                  // elect.sync: ptxas issues the TMA instructions straight from uniform registers
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
           if (!A_MN) {
             tma_load_2d_pair(sa, &tma_a, bar, k0, m0);
@@ -235,6 +253,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      int kbi = 0;
       for (int w = pair_id; w < p.total_work; w += num_pairs) {
         const Work2 it = decode_work2(p, w);
         const int kb_begin = it.kb_begin, kb_end = it.kb_end;
@@ -244,15 +263,24 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after_sync();
+          if (stamp && L && kbi < 1024) p.tl[4 * kbi + 1] = clock64();
           const uint64_t soff = static_cast<uint64_t>(stage * (Cfg::kStageBytes >> 4));
+          // elect.sync (not `lane == 0`) tells ptxas that exactly one lane issues: it then emits four back-to-back
+          // predicated UTCHMMAs on uniform registers.  Under a lane-id branch every MMA is wrapped in an
+          // elect/broadcast/retry loop whose latency (≈110 cycles per MMA, 670 per K block) — not the tensor pipe
+          // (512) — paced the main loop, for N = 128 and N = 256 alike.
+          if (elect_one()) {
+            if (!(p.dbg & 16)) {
 #pragma unroll
-          for (int k = 0; k < k2BK / 16; ++k)
-            if (L && !(p.dbg & 16)) tc_mma_bf16_pair(d_tmem, a_desc0 + soff + k * a_kstep, b_desc0 + soff + k * b_kstep, idesc,
-                                    (kb > kb_begin || k > 0) ? 1u : 0u);
-          if (L) {
+              for (int k = 0; k < k2BK / 16; ++k)
+                tc_mma_bf16_pair(d_tmem, a_desc0 + soff + k * a_kstep, b_desc0 + soff + k * b_kstep, idesc,
+                                 (kb > kb_begin || k > 0) ? 1u : 0u);
+            }
             tc_commit_pair(&empty_bar[stage], 3);                         // both CTAs' producers may refill
             if (kb == kb_end - 1) tc_commit_pair(&acc_full[acc], 3);   // both CTAs' epilogues may drain
           }
+          if (stamp && L && kbi < 1024) p.tl[4 * kbi + 2] = clock64();
+          ++kbi;
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
         acc ^= 1;
@@ -279,7 +307,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
                                                 epi == VITK_EPI_BIAS_GELUG_BF16 || epi == VITK_EPI_BIAS_RESID_F32);
     const int cw = out_f32 ? 16 : 32;                      // chunk width in columns
     const int nchunks = (BN / 2) / cw;
-    const int nout = has_aux ? 1 : 2;                      // output slabs in the ring (the last slab transposes aux)
+    const int nout = has_aux ? k2Slabs - 1 : k2Slabs;      // output slabs in the ring (the last slab transposes aux)
     const int aux_esize = out_f32 ? 4 : 2;
     const uint32_t acc_empty_leader = smem_u32(&acc_empty[0]) & 0xFEFFFFFFu;
     int acc = 0;
@@ -314,14 +342,14 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     auto emit = [&](const CUtensorMap* map, int col, int row0, const uint4 (&q)[4]) {
       if (p.dbg & 1) return;
       // wait until the store issued `nout` stores ago has finished reading its slab, then reuse it
-      if (lane == 0) { if (nout == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
+      if (elect_one()) { if (nout == k2Slabs) tma_store_wait_read<k2Slabs - 1>(); else tma_store_wait_read<k2Slabs - 2>(); }
       __syncwarp();
       uint8_t* slab = slabs + oslot * 2048;
 #pragma unroll
       for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(slab + slab16_off(lane, j)) = q[j];
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) {
+      if (elect_one()) {
         if (epi == VITK_EPI_ACCUM_F32) tma_reduce_add_2d(map, slab, col, row0);
         else tma_store_2d(map, slab, col, row0);
         tma_store_commit();
@@ -339,6 +367,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     };
 
     int w = pair_id;
+    int ti = 0;
     if (has_aux) {
       int r0, cc;
       if (chunk_after(w, 0, 0, &r0, &cc)) load_aux(axA, r0, cc);
@@ -360,6 +389,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       }
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after_sync();
+      if (stamp && ew == 0 && lane == 0 && ti < 256) p.tl[4096 + 4 * ti] = clock64();
       if (has_bias) {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -384,7 +414,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
         }
         uint4 arow[4] = {};  // this thread's row of the aux chunk (64 B)
         if (has_aux) {
-          uint8_t* tslab = slabs + 2048;
+          uint8_t* tslab = slabs + (k2Slabs - 1) * 2048;
           if (axi == 0) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(tslab + slab16_off(8 * i + rc, jc)) = axA[i];
@@ -489,8 +519,10 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
+      if (stamp && ew == 0 && lane == 0 && ti < 256) p.tl[4096 + 4 * ti + 1] = clock64();
+      ++ti;
     }
-    if (lane == 0) tma_store_wait_all<0>();   // smem must outlive the bulk reads; writes complete before exit
+    if (elect_one()) tma_store_wait_all<0>();   // smem must outlive the bulk reads; writes complete before exit
   }
   __syncwarp();
 
@@ -632,6 +664,7 @@ int gemm2_try_launch(const vitk_gemm_args& a, cudaStream_t stream, bool* handled
   p.aux = a.aux;
   p.ld_aux = a.ld_aux;
   p.bias = a.bias;
+  p.tl = g_timeline;
   const int pairs = p.total_work < pairs_avail ? p.total_work : pairs_avail;
   *handled = true;
   switch (bn) {

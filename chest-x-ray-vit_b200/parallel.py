@@ -19,12 +19,16 @@ import torch.distributed as dist
 
 class GradSync:
     def __init__(self, layer_ranges: Sequence[Tuple[int, int]], rest_ranges: Sequence[Tuple[int, int]],
-                 process_group: Optional[dist.ProcessGroup] = None, layers_per_bucket: int = 3):
+                 process_group: Optional[dist.ProcessGroup] = None, layers_per_bucket=3):
         self.layer_ranges = list(layer_ranges)
         self.rest_ranges = list(rest_ranges)
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
-        self.layers_per_bucket = max(1, layers_per_bucket)
+        # int: uniform buckets; sequence: bucket sizes in the order the layers finish (top layer first), the last
+        # entry repeating — e.g. (3, 3, 3, 2, 1) tapers the buckets so the all-reduce left after backward is short
+        sizes = [layers_per_bucket] if isinstance(layers_per_bucket, int) else list(layers_per_bucket)
+        self.bucket_sizes = [max(1, int(x)) for x in sizes] or [3]
+        self.bucket_index = 0
         self.flat: Optional[torch.Tensor] = None
         self.works: List = []
         self.pending: List[int] = []
@@ -32,7 +36,7 @@ class GradSync:
         self.collectives = 0
 
     @classmethod
-    def attach(cls, model, process_group=None, layers_per_bucket: int = 3) -> "GradSync":
+    def attach(cls, model, process_group=None, layers_per_bucket=3) -> "GradSync":
         gs = cls(model.layout.layer_range, model.layout.rest_ranges, process_group, layers_per_bucket)
         eng = model.engine()
         eng.grad_sync = gs
@@ -43,15 +47,18 @@ class GradSync:
     def begin(self, model_or_flat) -> None:
         self.flat = model_or_flat if isinstance(model_or_flat, torch.Tensor) else model_or_flat.flat_grads()
         self.works, self.pending = [], []
+        self.bucket_index = 0
 
     def layer_ready(self, l: int) -> None:
         """Layer ``l``'s weight gradients are enqueued on the current stream (layers finish in
         descending order).  Adjacent layers are coalesced into one contiguous bucket."""
         self.pending.append(l)
-        if len(self.pending) >= self.layers_per_bucket or l == 0:
+        size = self.bucket_sizes[min(self.bucket_index, len(self.bucket_sizes) - 1)]
+        if len(self.pending) >= size or l == 0:
             lo, hi = min(self.pending), max(self.pending)
             self._reduce(self.layer_ranges[lo][0], self.layer_ranges[hi][1])
             self.pending = []
+            self.bucket_index += 1
 
     def rest_ready(self) -> None:
         for s, e in self.rest_ranges:

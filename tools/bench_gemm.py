@@ -58,9 +58,19 @@ CASES = [
 
 
 def run(c, reps=10, **kw):
-    def go():
+    if kw.get("cublas"):        # torch.matmul (cuBLASLt), no epilogue: the library's number for the same shape, for reference
+        a2 = c["a"].t() if c["a_mn"] else c["a"]
+        b2 = c["b"] if c["b_mn"] else c["b"].t()
+        out = torch.empty(c["M"], c["N"], device=dev, dtype=bf16)
+
+        def go():
+            torch.matmul(a2, b2, out=out)
+    else:
+        go = None
+    def go_vitk():
         ops.gemm(c["a"], c["b"], c["M"], c["N"], c["K"], c["d"], epilogue=c["epi"], a_mn_major=c["a_mn"], b_mn_major=c["b_mn"],
                  **c["extra"], **kw)
+    go = go or go_vitk
     for _ in range(2):
         go()
     ts = []
@@ -79,6 +89,10 @@ def run(c, reps=10, **kw):
 configs = [dict(variant=1), dict(variant=2), dict(variant=2, tile_n=128), dict(variant=2, tile_n=192), dict(variant=2, tile_n=256)]
 if len(sys.argv) > 1 and sys.argv[1] == "--quick":
     configs = [dict(variant=2), dict(variant=2, tile_n=256)]
+if len(sys.argv) > 1 and sys.argv[1] == "--cublas":
+    configs = [dict(variant=2), dict(cublas=True)]
+if len(sys.argv) > 1 and sys.argv[1] == "--none":         # imported as a module (tools/gemm_timeline.py)
+    configs = []
 if len(sys.argv) > 1 and sys.argv[1] == "--profile":      # one launch per case, default tiling (for ncu)
     for c in CASES:
         ops.gemm(c["a"], c["b"], c["M"], c["N"], c["K"], c["d"], epilogue=c["epi"], a_mn_major=c["a_mn"], b_mn_major=c["b_mn"],
@@ -90,9 +104,13 @@ if len(sys.argv) > 1 and sys.argv[1] == "--profile":      # one launch per case,
                  **c["extra"])
     torch.cuda.synchronize()
     sys.exit(0)
+if not configs:
+    CASES_TO_RUN = []
+else:
+    CASES_TO_RUN = CASES
 print(f"{'gemm':14s} {'M':>5s} {'N':>5s} {'K':>5s} | " + " | ".join(f"{str(k):>24s}" for k in configs))
 tot = [0.0] * len(configs)
-for c in CASES:
+for c in CASES_TO_RUN:
     fl = 2.0 * c["M"] * c["N"] * c["K"]
     cells = []
     for i, k in enumerate(configs):

@@ -1,0 +1,78 @@
+"""Per-K-block clock64 timeline of the leader CTA of pair 0 of the CTA-pair GEMM (vitk_debug_timeline stamps):
+when the producer got a free stage, when the MMA warp saw it full, when the MMAs were issued, and when the
+epilogue started / finished each tile.  Usage: python tools/gemm_timeline.py [case-substring ...]"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.argv, argv = sys.argv[:1] + ["--none"], sys.argv[1:]
+import bench_gemm as bg  # noqa: E402  (builds CASES; "--none" keeps it from running its table)
+
+pkg, ops = bg.pkg, bg.ops
+lib = pkg._lib.lib()
+
+
+KW = {}
+for a_ in argv:
+    if a_.startswith("--tile_n="):
+        KW["tile_n"] = int(a_.split("=")[1])
+
+
+def timeline(c, flush):
+    tl = torch.zeros(8192, dtype=torch.int64, device="cuda")
+
+    def go():
+        ops.gemm(c["a"], c["b"], c["M"], c["N"], c["K"], c["d"], epilogue=c["epi"], a_mn_major=c["a_mn"], b_mn_major=c["b_mn"],
+                 **c["extra"], **KW)
+    go()
+    if flush:
+        bg.flush.fill_(1)
+    torch.cuda.synchronize()
+    lib.vitk_debug_timeline(tl.data_ptr())
+    go()
+    torch.cuda.synchronize()
+    lib.vitk_debug_timeline(None)
+    return tl.cpu().tolist()
+
+
+def report(c, flush):
+    t = timeline(c, flush)
+    P = [t[4 * i] for i in range(1024) if t[4 * i]]
+    F = [t[4 * i + 1] for i in range(1024) if t[4 * i + 1]]
+    I = [t[4 * i + 2] for i in range(1024) if t[4 * i + 2]]
+    E0 = [t[4096 + 4 * i] for i in range(256) if t[4096 + 4 * i]]
+    E1 = [t[4096 + 4 * i + 1] for i in range(256) if t[4096 + 4 * i + 1]]
+    n = min(len(P), len(F), len(I))
+    t0 = P[0]
+    print(f"=== {c['name'].strip()}  M={c['M']} N={c['N']} K={c['K']}  L2 {'flushed' if flush else 'warm'}: {n} K blocks, {len(E0)} tiles, "
+          f"span {max(E1) - t0 if E1 else 0} cycles")
+    kb_per_tile = n // max(len(E0), 1)
+    cad = [F[i + 1] - F[i] for i in range(n - 1)]
+    lat = [F[i] - P[i] for i in range(n)]
+    iss = [I[i] - F[i] for i in range(n)]
+    print(f"   first stage: request→full {lat[0]}   cadence (full→full) median {sorted(cad)[len(cad) // 2]}  mean {sum(cad) / len(cad):.0f}  "
+          f"max {max(cad)}   issue median {sorted(iss)[len(iss) // 2]}")
+    print(f"   request→full by K block (first 14): {lat[:14]}")
+    print(f"   request→full median {sorted(lat)[len(lat) // 2]}  producer stamp gap median {sorted(P[i + 1] - P[i] for i in range(n - 1))[(n - 1) // 2]}")
+    for ti in range(len(E0)):
+        kb0 = ti * kb_per_tile
+        hi = min(kb0 + kb_per_tile, n)
+        tc = sorted(F[i + 1] - F[i] for i in range(kb0, hi - 1))
+        tis = sorted(I[i] - F[i] for i in range(kb0, hi))
+        tl_ = sorted(F[i] - P[i] for i in range(kb0, hi))
+        print(f"   tile {ti}: cadence median {tc[len(tc) // 2] if tc else 0}  issue median {tis[len(tis) // 2]}  request→full median {tl_[len(tl_) // 2]}")
+        print(f"   tile {ti}: first K block full {F[kb0] - t0:7d}  last MMA issued {I[min(kb0 + kb_per_tile, n) - 1] - t0:7d}  "
+              f"epilogue start {E0[ti] - t0:7d}  end {E1[ti] - t0:7d}  (epilogue {E1[ti] - E0[ti]})")
+    if "-v" in argv:
+        for i in range(n):
+            print(f"      kb {i:3d}  P {P[i] - t0:7d}  F {F[i] - t0:7d}  I {I[i] - t0:7d}")
+
+
+sel = [a for a in argv if not a.startswith("-")]
+for c in bg.CASES:
+    if sel and not any(s in c["name"] for s in sel):
+        continue
+    for flush in (True, False):
+        report(c, flush)
