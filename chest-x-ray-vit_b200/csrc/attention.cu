@@ -132,22 +132,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
 
   if (warp == 4) {
     // ------------------------------------------------------------------ control warp: TMA + MMA issue
-    // Every lane runs this loop so that descriptors and addresses stay warp-uniform (uniform registers);
-    // only the issuing instructions themselves are predicated on lane 0.  With the whole block under
-    // `if (lane == 0)` each MMA cost ~100 cycles of single-thread descriptor arithmetic + R2UR moves,
-    // several times the 32–64 cycles the MMA occupies the tensor core.
-    const bool L = lane == 0;
+    // Every lane runs this loop so that descriptors and addresses stay warp-uniform (uniform registers), and the
+    // issuing instructions sit under elect.sync: ptxas then knows exactly one lane issues and emits back-to-back
+    // UTCHMMA / UTMALDG on uniform registers.  Under a lane-id test (`lane == 0`) every MMA is wrapped in an
+    // elect/broadcast/retry loop costing ≈100 cycles — several times the 49 cycles an N = 64 MMA occupies the pipe.
     {
       auto load_kv = [&](int u) {
         const int buf = u & 1;
-        if (L) {
+        if (elect_one()) {
           mbar_arrive_expect_tx(&bar_k[buf], kSubBytes);
           tma_load_3d(sK + buf * kSubBytes, &tma_kv, &bar_k[buf], colk, u * kSub, b);
           mbar_arrive_expect_tx(&bar_v[buf], kSubBytes);
           tma_load_3d(sV + buf * kSubBytes, &tma_kv, &bar_v[buf], colv, u * kSub, b);
         }
       };
-      if (L) {
+      if (elect_one()) {
         mbar_arrive_expect_tx(bar_q, kTileBytes);
         tma_load_3d(sQ, &tma_q, bar_q, colq, qb * kTile, b);
       }
@@ -163,10 +162,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
         tc_fence_after_sync();
         const uint64_t bk = k_desc + static_cast<uint64_t>(buf * (kSubBytes >> 4));
         const uint32_t idesc_s = umma_idesc_bf16(kTile, sub_cols(u), 0, 0);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < kDh / 16; ++k)
-          if (L) tc_mma_bf16(tmem_base, q_desc + 2 * k, bk + 2 * k, idesc_s, k > 0);
-        if (L) tc_commit(bar_s);
+          for (int k = 0; k < kDh / 16; ++k) tc_mma_bf16(tmem_base, q_desc + 2 * k, bk + 2 * k, idesc_s, k > 0);
+          tc_commit(bar_s);
+        }
       };
       mbar_wait(bar_q, 0);
       issue_s(0);
@@ -179,9 +179,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
         tc_fence_after_sync();
         const uint64_t bv = v_desc + static_cast<uint64_t>(buf * (kSubBytes >> 4));
         const int ksteps = sub_cols(u) / 16;
-        for (int k = 0; k < ksteps; ++k)
-          if (L) tc_mma_bf16_ts(tmem_o, tmem_base + k * 8, bv + k * 128, idesc_pv, (u > 0 || k > 0) ? 1u : 0u);
-        if (L) {
+        if (elect_one()) {
+          if (ksteps == kSub / 16) {           // full sub-block: unrolled, MMAs issue back to back
+#pragma unroll
+            for (int k = 0; k < kSub / 16; ++k)
+              tc_mma_bf16_ts(tmem_o, tmem_base + k * 8, bv + k * 128, idesc_pv, (u > 0 || k > 0) ? 1u : 0u);
+          } else {
+            for (int k = 0; k < ksteps; ++k)
+              tc_mma_bf16_ts(tmem_o, tmem_base + k * 8, bv + k * 128, idesc_pv, (u > 0 || k > 0) ? 1u : 0u);
+          }
           tc_commit(bar_pv);
           tc_commit(&bar_free[buf]);
           if (u == nsub - 1) tc_commit(bar_o);
@@ -442,9 +448,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
 
   if (warp == kBwdComputeWarps) {
     // ------------------------------------------------------------------ control warp: TMA + MMA issue
-    // (all lanes run the loop so descriptors stay in uniform registers; only the issuing instructions are
-    // predicated on lane 0)
-    const bool L = lane == 0;
+    // (all lanes run the loop so descriptors stay in uniform registers; the issuing instructions sit under
+    // elect.sync so that ptxas emits them back to back instead of one elect/broadcast/retry loop per instruction)
     constexpr uint32_t idesc_sc = umma_idesc_bf16(kTile, kQSub, 0, 0);  // Sᵀ = K·Qᵀ, dPᵀ = V·dOᵀ (N = 64 queries)
     constexpr uint32_t idesc_km = umma_idesc_bf16(kTile, kDh, 0, 1);    // dV += Pᵀ·dO, dK += dSᵀ·Q
     constexpr uint32_t idesc_mm = umma_idesc_bf16(kTile, kDh, 1, 1);    // dQ = dS·K
@@ -460,7 +465,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
     const uint64_t dst_mnmaj = umma_smem_desc(smem_u32(sDSt), kTileBytes, 1024);
     auto load_qd = [&](int u) {              // sub-block u → ring slot u&3
       const int slot = u & 3;
-      if (L) {
+      if (elect_one()) {
         mbar_arrive_expect_tx(&bar_qd[slot], 2 * kQSub * 128);
         tma_load_3d(sQ + slot * (kQSub * 128), &tma_q64, &bar_qd[slot], colq, u * kQSub, b);
         tma_load_3d(sDO + slot * (kQSub * 128), &tma_do64, &bar_qd[slot], colq, u * kQSub, b);
@@ -472,15 +477,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
       mbar_wait(&bar_qd[u & 3], (u >> 2) & 1);
       tc_fence_after_sync();
       const uint32_t t_s = tmem_base + x * 128, t_dp = t_s + 64;
+      if (elect_one()) {
 #pragma unroll
-      for (int k = 0; k < kDh / 16; ++k)
-        if (L) tc_mma_bf16(t_s, k_kmaj + 2 * k, q_kmaj + boff + 2 * k, idesc_sc, k > 0);
+        for (int k = 0; k < kDh / 16; ++k) tc_mma_bf16(t_s, k_kmaj + 2 * k, q_kmaj + boff + 2 * k, idesc_sc, k > 0);
 #pragma unroll
-      for (int k = 0; k < kDh / 16; ++k)
-        if (L) tc_mma_bf16(t_dp, v_kmaj + 2 * k, do_kmaj + boff + 2 * k, idesc_sc, k > 0);
-      if (L) tc_commit(&bar_s[x]);
+        for (int k = 0; k < kDh / 16; ++k) tc_mma_bf16(t_dp, v_kmaj + 2 * k, do_kmaj + boff + 2 * k, idesc_sc, k > 0);
+        tc_commit(&bar_s[x]);
+      }
     };
-    if (L) {
+    if (elect_one()) {
       mbar_arrive_expect_tx(bar_kv, 2 * kTileBytes);
       tma_load_3d(sK, &tma_qkv, bar_kv, colk, key0, b);
       tma_load_3d(sV, &tma_qkv, bar_kv, colv, key0, b);
@@ -496,20 +501,22 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
       VITK_STAMP(16 * u + 0);
       tc_fence_after_sync();
       const uint32_t t_p = tmem_base + x * 128, t_ds = t_p + 64;
-#pragma unroll
-      for (int k = 0; k < kQSub / 16; ++k)   // dV[key,d] += Σ_q Pᵀ[key,q]·dO[q,d]; Pᵀ of column group k sits at Sᵀ column 16k
-        if (L) tc_mma_bf16_ts(tm_dv, t_p + 16 * k, do_mnmaj + boff + 128 * k, idesc_km, (u > 0 || k > 0) ? 1u : 0u);
-#pragma unroll
-      for (int k = 0; k < kQSub / 16; ++k)   // dK[key,d] += Σ_q dSᵀ[key,q]·Q[q,d]
-        if (L) tc_mma_bf16_ts(tm_dk, t_ds + 16 * k, q_mnmaj + boff + 128 * k, idesc_km, (u > 0 || k > 0) ? 1u : 0u);
-      if (L) tc_commit(&bar_free[u & 3]);
       const bool block_done = hq == 1 || u == nsub - 1;
-      if (block_done) {
+      if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < kTile / 16; ++k)   // dQ[q,d] = Σ_key dS[q,key]·K[key,d]; A = dSᵀ smem tile read MN-major
-          if (L) tc_mma_bf16(tm_dq + (i & 1) * kDh, dst_mnmaj + static_cast<uint64_t>((i & 1) * 2 * kTile16) + 128 * k,
-                             k_mnmaj + 128 * k, idesc_mm, k > 0);
-        if (L) tc_commit(bar_g);
+        for (int k = 0; k < kQSub / 16; ++k)   // dV[key,d] += Σ_q Pᵀ[key,q]·dO[q,d]; Pᵀ of column group k sits at Sᵀ column 16k
+          tc_mma_bf16_ts(tm_dv, t_p + 16 * k, do_mnmaj + boff + 128 * k, idesc_km, (u > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < kQSub / 16; ++k)   // dK[key,d] += Σ_q dSᵀ[key,q]·Q[q,d]
+          tc_mma_bf16_ts(tm_dk, t_ds + 16 * k, q_mnmaj + boff + 128 * k, idesc_km, (u > 0 || k > 0) ? 1u : 0u);
+        tc_commit(&bar_free[u & 3]);
+        if (block_done) {
+#pragma unroll
+          for (int k = 0; k < kTile / 16; ++k)   // dQ[q,d] = Σ_key dS[q,key]·K[key,d]; A = dSᵀ smem tile read MN-major
+            tc_mma_bf16(tm_dq + (i & 1) * kDh, dst_mnmaj + static_cast<uint64_t>((i & 1) * 2 * kTile16) + 128 * k,
+                        k_mnmaj + 128 * k, idesc_mm, k > 0);
+          tc_commit(bar_g);
+        }
       }
       VITK_STAMP(16 * u + 1);
       if (u + 2 < nsub) issue_scores(u + 2);   // queued right behind: MMAs retire in issue order
@@ -534,7 +541,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
     auto reduce_dq = [&](int i) {
       uint32_t r[16];
       tmem_ld_32x16(tm_dq + (i & 1) * kDh + lane_field + cg * 16, r);
-      if (lane == 0) tma_store_wait_read<0>();     // previous block's reduce has finished reading the slab
+      if (elect_one()) tma_store_wait_read<0>();   // previous block's reduce has finished reading the slab
       __syncwarp();
       tmem_ld_wait();
 #pragma unroll
@@ -543,7 +550,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
             make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) {
+      if (elect_one()) {
         tma_reduce_add_3d(&tma_dq, dq_slab, h * kDh + cg * 16, i * kTile + quad * 32, b);
         tma_store_commit();
       }
@@ -612,7 +619,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
     mbar_wait(bar_g, (nq - 1) & 1);
     tc_fence_after_sync();
     reduce_dq(nq - 1);
-    if (lane == 0) tma_store_wait_all<0>();
+    if (elect_one()) tma_store_wait_all<0>();
     // dV (cg 0,1) and dK·scale (cg 2,3) → dqkv[b, key, 2|1, h, :]
     {
       const bool is_dv = cg < 2;

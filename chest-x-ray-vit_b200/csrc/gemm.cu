@@ -214,7 +214,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // (all lanes run the loop; the issue sits under elect.sync so ptxas emits the TMA instructions on uniform
+    // registers instead of one elect/broadcast/retry loop per instruction)
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
@@ -224,19 +226,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + kABytes;
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           const int k0 = kb * kBK;
-          if (!A_MN) {
-            tma_load_2d(sa, &tma_a, &full_bar[stage], k0, m0);
-          } else {
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            if (!A_MN) {
+              tma_load_2d(sa, &tma_a, &full_bar[stage], k0, m0);
+            } else {
 #pragma unroll
-            for (int g = 0; g < kBM / 64; ++g) tma_load_2d(sa + g * 8192, &tma_a, &full_bar[stage], m0 + g * 64, k0);
-          }
-          if (!B_MN) {
-            tma_load_2d(sb, &tma_b, &full_bar[stage], k0, n0);
-          } else {
+              for (int g = 0; g < kBM / 64; ++g) tma_load_2d(sa + g * 8192, &tma_a, &full_bar[stage], m0 + g * 64, k0);
+            }
+            if (!B_MN) {
+              tma_load_2d(sb, &tma_b, &full_bar[stage], k0, n0);
+            } else {
 #pragma unroll
-            for (int g = 0; g < BN / 64; ++g) tma_load_2d(sb + g * 8192, &tma_b, &full_bar[stage], n0 + g * 64, k0);
+              for (int g = 0; g < BN / 64; ++g) tma_load_2d(sb + g * 8192, &tma_b, &full_bar[stage], n0 + g * 64, k0);
+            }
           }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -259,7 +263,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       for (int kb = it.kb_begin; kb < it.kb_end; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after_sync();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
           const uint32_t sb = sa + kABytes;
 #pragma unroll
