@@ -64,6 +64,8 @@ struct Cfg2 {
 struct Gemm2Params {
   int M, N, K;
   int n_tiles, mn_tiles, k_splits, kb_per_split, kb_total, total_work;
+  int n_full, n_half;  // every 256-row band is cut into n_full tiles of BN columns followed by n_half tiles of BN/2 columns
+                       // (n_tiles = n_full + n_half); all full tiles come first in the work order
   int epi;
   int has_d2;
   int dbg;            // VITK_GEMM_DBG experiment bits (0 in production): 1 skip stores, 2 skip aux, 4 skip TMEM loads,
@@ -79,14 +81,24 @@ struct Gemm2Params {
 extern long long* g_timeline;
 
 struct Work2 {
-  int m_blk, n_blk, kb_begin, kb_end;
+  int m_blk, n0, bn, kb_begin, kb_end;   // n0: first output column, bn: tile width (BN or BN/2)
 };
+template <int BN>
 __device__ __forceinline__ Work2 decode_work2(const Gemm2Params& p, int w) {
   const int ks = w / p.mn_tiles;
   const int t = w - ks * p.mn_tiles;
   Work2 it;
-  it.m_blk = t / p.n_tiles;
-  it.n_blk = t - it.m_blk * p.n_tiles;
+  const int full_items = (p.mn_tiles / p.n_tiles) * p.n_full;
+  if (t < full_items) {
+    it.m_blk = t / p.n_full;
+    it.n0 = (t - it.m_blk * p.n_full) * BN;
+    it.bn = BN;
+  } else {
+    const int th = t - full_items;
+    it.m_blk = th / p.n_half;
+    it.n0 = p.n_full * BN + (th - it.m_blk * p.n_half) * (BN / 2);
+    it.bn = BN / 2;
+  }
   it.kb_begin = ks * p.kb_per_split;
   it.kb_end = min(it.kb_begin + p.kb_per_split, p.kb_total);
   return it;
@@ -147,6 +159,7 @@ __device__ __forceinline__ void add_bias32(const float* __restrict__ bias, int c
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                  const __grid_constant__ CUtensorMap tma_bh,   // K-major B, box of BN/4 rows (half-width tiles)
                   const __grid_constant__ CUtensorMap tma_d, const __grid_constant__ CUtensorMap tma_d2,
                   const Gemm2Params p) {
   using Cfg = Cfg2<BN>;
@@ -175,6 +188,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
+    if (p.n_half > 0 && !B_MN) tma_prefetch_desc(&tma_bh);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -207,9 +221,11 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     uint32_t phase = 0;
     int kbi = 0;
     for (int w = pair_id; w < p.total_work; w += num_pairs) {
-      const Work2 it = decode_work2(p, w);
+      const Work2 it = decode_work2<BN>(p, w);
       const int m0 = (p.dbg & 8) ? 0 : it.m_blk * (2 * k2BM) + static_cast<int>(cta_rank) * k2BM;
-      const int n0 = (p.dbg & 8) ? 0 : it.n_blk * BN + static_cast<int>(cta_rank) * kBHalf;
+      const bool half = it.bn != BN;                  // half-width tile: this CTA stages BN/4 rows of B
+      const int n0 = (p.dbg & 8) ? 0 : it.n0 + static_cast<int>(cta_rank) * (it.bn >> 1);
+      const uint32_t stage_tx = 2 * (k2ABytes + (half ? Cfg::kBBytes / 2 : Cfg::kBBytes));
       const int kb_begin = it.kb_begin, kb_end = it.kb_end;
       for (int kb = kb_begin; kb < kb_end; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -222,7 +238,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
         if ((p.dbg & 32) && kbi > kStages) {       // experiment: MMAs re-read stale stages, no TMA traffic at all
           if (L && leader) mbar_arrive(&full_bar[stage]);
         } else if (elect_one()) {                  // elect.sync: ptxas issues the TMA instructions straight from uniform registers
-          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
           if (!A_MN) {
             tma_load_2d_pair(sa, &tma_a, bar, k0, m0);
           } else {
@@ -230,10 +246,12 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
             for (int g = 0; g < k2BM / 64; ++g) tma_load_2d_pair(sa + g * 8192, &tma_a, bar, m0 + g * 64, k0);
           }
           if (!B_MN) {
-            tma_load_2d_pair(sb, &tma_b, bar, k0, n0);
+            if (half) tma_load_2d_pair(sb, &tma_bh, bar, k0, n0);
+            else tma_load_2d_pair(sb, &tma_b, bar, k0, n0);
           } else {
 #pragma unroll
-            for (int g = 0; g < kBHalf / 64; ++g) tma_load_2d_pair(sb + g * 8192, &tma_b, bar, n0 + g * 64, k0);
+            for (int g = 0; g < kBHalf / 64; ++g)
+              if (!half || g < kBHalf / 128) tma_load_2d_pair(sb + g * 8192, &tma_b, bar, n0 + g * 64, k0);
           }
         }
         if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -244,7 +262,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
     if (leader) {
       const bool L = lane == 0;
-      constexpr uint32_t idesc = umma_idesc_bf16(2 * k2BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      constexpr uint32_t idesc_full = umma_idesc_bf16(2 * k2BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      constexpr uint32_t idesc_half = umma_idesc_bf16(2 * k2BM, BN / 2, A_MN ? 1 : 0, B_MN ? 1 : 0);
       constexpr uint32_t a_lbo = A_MN ? 8192u : 0u, b_lbo = B_MN ? 8192u : 0u;
       constexpr uint32_t a_kstep = (A_MN ? 2048u : 32u) >> 4, b_kstep = (B_MN ? 2048u : 32u) >> 4;   // 16-byte units
       const uint64_t a_desc0 = umma_smem_desc(smem_u32(smem), a_lbo, 1024);
@@ -255,8 +274,9 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       uint32_t acc_phase = 0;
       int kbi = 0;
       for (int w = pair_id; w < p.total_work; w += num_pairs) {
-        const Work2 it = decode_work2(p, w);
+        const Work2 it = decode_work2<BN>(p, w);
         const int kb_begin = it.kb_begin, kb_end = it.kb_end;
+        const uint32_t idesc = it.bn == BN ? idesc_full : idesc_half;
         mbar_wait(&acc_empty[acc], acc_phase ^ 1);
         tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -306,7 +326,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     const bool has_bias = p.bias != nullptr && (epi == VITK_EPI_BIAS_BF16 || epi == VITK_EPI_BIAS_GELU_BF16 ||
                                                 epi == VITK_EPI_BIAS_GELUG_BF16 || epi == VITK_EPI_BIAS_RESID_F32);
     const int cw = out_f32 ? 16 : 32;                      // chunk width in columns
-    const int nchunks = (BN / 2) / cw;
+    const int cshift = out_f32 ? 4 : 5;                    // log2(cw)
     const int nout = has_aux ? k2Slabs - 1 : k2Slabs;      // output slabs in the ring (the last slab transposes aux)
     const int aux_esize = out_f32 ? 4 : 2;
     const uint32_t acc_empty_leader = smem_u32(&acc_empty[0]) & 0xFEFFFFFFu;
@@ -316,7 +336,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     const int rc = lane >> 2, jc = lane & 3;               // coalesced layout: iteration i ↔ row 8i + rc, 16-byte chunk jc
 
     auto tile_row0 = [&](const Work2& it) { return it.m_blk * (2 * k2BM) + static_cast<int>(cta_rank) * k2BM + quad * 32; };
-    auto tile_col0 = [&](const Work2& it) { return it.n_blk * BN + col_half * (BN / 2); };
+    auto tile_col0 = [&](const Work2& it) { return it.n0 + col_half * (it.bn >> 1); };   // this warp's column half of the tile
 
     uint4 axA[4], axB[4];  // aux chunks in flight (coalesced layout); named, never indexed dynamically, so they stay in registers
     auto load_aux = [&](uint4 (&dst)[4], int row0, int col) {
@@ -329,14 +349,19 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
                                     : make_uint4(0, 0, 0, 0);
       }
     };
-    // coordinates of the chunk `ahead` chunks after (w, c); false when past this CTA's last tile
-    auto chunk_after = [&](int w, int c, int ahead, int* row0, int* col) {
+    // coordinates of the chunk `ahead` (≤ 2) chunks after chunk c of tile `cur`; `nxt` is this CTA's next tile
+    // (every tile has ≥ 2 chunks, so the look-ahead never reaches past it); false when past the last tile
+    auto chunk_after = [&](const Work2& cur, const Work2& nxt, bool has_next, int c, int ahead, int* row0, int* col) {
       c += ahead;
-      while (c >= nchunks) { c -= nchunks; w += num_pairs; }
-      if (w >= p.total_work) return false;
-      const Work2 nt = decode_work2(p, w);
-      *row0 = tile_row0(nt);
-      *col = tile_col0(nt) + c * cw;
+      const int nch = (cur.bn >> 1) >> cshift;
+      if (c < nch) {
+        *row0 = tile_row0(cur);
+        *col = tile_col0(cur) + c * cw;
+        return true;
+      }
+      if (!has_next) return false;
+      *row0 = tile_row0(nxt);
+      *col = tile_col0(nxt) + (c - nch) * cw;
       return true;
     };
     auto emit = [&](const CUtensorMap* map, int col, int row0, const uint4 (&q)[4]) {
@@ -368,15 +393,19 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
 
     int w = pair_id;
     int ti = 0;
-    if (has_aux) {
+    Work2 it = decode_work2<BN>(p, w < p.total_work ? w : 0);
+    if (has_aux && w < p.total_work) {
       int r0, cc;
-      if (chunk_after(w, 0, 0, &r0, &cc)) load_aux(axA, r0, cc);
-      if (chunk_after(w, 0, 1, &r0, &cc)) load_aux(axB, r0, cc);
+      if (chunk_after(it, it, false, 0, 0, &r0, &cc)) load_aux(axA, r0, cc);
+      if (chunk_after(it, it, false, 0, 1, &r0, &cc)) load_aux(axB, r0, cc);
     }
     int axi = 0;   // 0: axA holds the current chunk's aux, 1: axB
     for (; w < p.total_work; w += num_pairs) {
-      const Work2 it = decode_work2(p, w);
+      const bool has_next = w + num_pairs < p.total_work;
+      const Work2 nxt = decode_work2<BN>(p, has_next ? w + num_pairs : w);
       const int row0 = tile_row0(it), col0 = tile_col0(it);
+      const int half_w = it.bn >> 1;                       // columns of this tile that belong to this warp's column half
+      const int nchunks = half_w >> cshift;
       // This column half's BN/2 bias values: fetched before the wait, published to smem after it.  The slice is
       // shared by the 4 quadrant warps (identical values) and double-buffered by tile parity; a warp past
       // acc_full(t) knows every warp finished READING the bias of tile t−2, because those reads precede the
@@ -385,7 +414,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       float bpre[4];
       if (has_bias) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) bpre[i] = (lane + 32 * i < BN / 2) ? __ldg(p.bias + col0 + lane + 32 * i) : 0.f;
+        for (int i = 0; i < 4; ++i) bpre[i] = (lane + 32 * i < half_w) ? __ldg(p.bias + col0 + lane + 32 * i) : 0.f;
       }
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after_sync();
@@ -393,10 +422,10 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       if (has_bias) {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-          if (lane + 32 * i < BN / 2) bias_s[lane + 32 * i] = bpre[i];
+          if (lane + 32 * i < half_w) bias_s[lane + 32 * i] = bpre[i];
         __syncwarp();
       }
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + col_half * (BN / 2);
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + col_half * half_w;
 #pragma unroll 1
       for (int c = 0; c < nchunks; ++c) {
         const int col = col0 + c * cw;
@@ -427,7 +456,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
           for (int j = 0; j < 4; ++j) arow[j] = *reinterpret_cast<const uint4*>(tslab + slab16_off(lane, j));
           __syncwarp();
           int r0, cc;
-          if (chunk_after(w, c, 2, &r0, &cc)) {   // refill the registers just consumed
+          if (chunk_after(it, nxt, has_next, c, 2, &r0, &cc)) {   // refill the registers just consumed
             if (axi == 0) load_aux(axA, r0, cc); else load_aux(axB, r0, cc);
           }
           axi ^= 1;
@@ -521,6 +550,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       if (acc == 0) acc_phase ^= 1;
       if (stamp && ew == 0 && lane == 0 && ti < 256) p.tl[4096 + 4 * ti + 1] = clock64();
       ++ti;
+      it = nxt;
     }
     if (elect_one()) tma_store_wait_all<0>();   // smem must outlive the bulk reads; writes complete before exit
   }
@@ -547,7 +577,7 @@ static int out_map(CUtensorMap* m, const void* base, bool f32, long long rows, l
 template <int BN, bool A_MN, bool B_MN>
 static int launch_gemm2(const vitk_gemm_args& a, const Gemm2Params& p, int pairs, cudaStream_t stream) {
   using Cfg = Cfg2<BN>;
-  CUtensorMap ta, tb, td, td2;
+  CUtensorMap ta, tb, tbh, td, td2;
   {
     uint64_t dims[2], str[1];
     uint32_t box[2];
@@ -559,6 +589,11 @@ static int launch_gemm2(const vitk_gemm_args& a, const Gemm2Params& p, int pairs
     else       { dims[0] = a.N; dims[1] = a.K; box[0] = 64;   box[1] = k2BK; }
     str[0] = static_cast<uint64_t>(a.ldb) * 2;
     if (int rc = make_tensor_map_bf16(&tb, a.b, 2, dims, str, box)) return rc;
+    tbh = tb;
+    if (!B_MN && p.n_half > 0) {       // half-width tiles stage BN/4 rows of a K-major B per CTA
+      box[1] = Cfg::kBHalfRows / 2;
+      if (int rc = make_tensor_map_bf16(&tbh, a.b, 2, dims, str, box)) return rc;
+    }
   }
   const bool f32_out = a.epilogue == VITK_EPI_BIAS_RESID_F32 || a.epilogue == VITK_EPI_ACCUM_F32 || a.epilogue == VITK_EPI_STORE_F32;
   if (int rc = out_map(&td, a.d, f32_out, a.M, a.N, a.ldd)) return rc;
@@ -571,7 +606,7 @@ static int launch_gemm2(const vitk_gemm_args& a, const Gemm2Params& p, int pairs
     attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
   });
   if (attr_err != cudaSuccess) return cuda_error(attr_err, "cudaFuncSetAttribute(gemm2 smem)");
-  if (cudaError_t e = launch_pdl(kern, dim3(2 * pairs), dim3(k2Threads), Cfg::kSmemBytes, stream, ta, tb, td, td2, p); e != cudaSuccess)
+  if (cudaError_t e = launch_pdl(kern, dim3(2 * pairs), dim3(k2Threads), Cfg::kSmemBytes, stream, ta, tb, tbh, td, td2, p); e != cudaSuccess)
     return cuda_error(e, "gemm2_bf16_kernel launch");
   VITK_LAUNCH_CHECK("gemm2_bf16_kernel");
   return 0;
@@ -593,10 +628,16 @@ static int dispatch_major2(const vitk_gemm_args& a, const Gemm2Params& p, int pa
 // reads of (16 KB of A + 64·BN bytes of B) per CTA — 512 / 448 / 384 cycles for BN = 256 / 192 / 128, so
 // narrow tiles are shared-memory-bound.  cost = waves × (K blocks × that + a per-tile fill/epilogue
 // constant); split-K (wgrad only) multiplies the work items until one wave is full.
-static void choose_tiling2(const vitk_gemm_args& a, int pairs, int* bn_out, int* splits_out) {
+// cycles a CTA pair spends per 64-wide K block of a tile of `bn` columns (tools/gemm_timeline.py, B200): the MMAs of a
+// 256-wide tile occupy the tensor pipe for 4 × 122 cycles; narrower tiles are bound by operand delivery instead
+static double kblock_cycles(int bn) { return bn == 256 ? 500.0 : (bn == 192 ? 440.0 : 390.0); }
+constexpr double kTileFixedCycles = 1500.0;   // accumulator hand-over + pipeline refill per tile
+
+static void choose_tiling2(const vitk_gemm_args& a, int pairs, int* bn_out, int* splits_out, int* n_half_out) {
   const long long mt = (a.M + 2 * k2BM - 1) / (2 * k2BM);
   const long long kb_total = (a.K + k2BK - 1) / k2BK;
   double best = 1e30;
+  static const int mixed_allowed = [] { const char* e = getenv("VITK_GEMM_MIXED"); return e ? atoi(e) : 1; }();
   const int cands[3] = {256, 192, 128};
   for (int bn : cands) {
     if (a.N % bn) continue;
@@ -616,10 +657,26 @@ static void choose_tiling2(const vitk_gemm_args& a, int pairs, int* bn_out, int*
     const long long kb_per = (kb_total + splits - 1) / splits;
     const long long items = tiles * ((kb_total + kb_per - 1) / kb_per);
     const long long waves = (items + pairs - 1) / pairs;
-    const double mma = 2.0 * bn, smem = (16384.0 + 64.0 * bn) * 2.0 / 128.0;
-    const double kblock = mma > smem ? mma : smem;
-    const double cost = static_cast<double>(waves) * (kb_per * kblock + 1500.0);
-    if (cost < best - 1e-9) { best = cost; *bn_out = bn; *splits_out = splits; }
+    const double cost = static_cast<double>(waves) * (kb_per * kblock_cycles(bn) + kTileFixedCycles);
+    if (cost < best - 1e-9) { best = cost; *bn_out = bn; *splits_out = splits; *n_half_out = 0; }
+    // Mixed widths (BN = 256 only): replace some of each band's 256-column tiles by pairs of 128-column tiles so that
+    // the static round-robin order gives every CTA pair the same amount of work (e.g. N = 768 on 74 pairs: 3 full
+    // tiles per band = 1.5 waves of full tiles; 2 full + 2 half = one full and one half tile for every pair).
+    if (bn == 256 && splits == 1 && a.epilogue != VITK_EPI_ACCUM_F32 && a.tile_n == 0 && mixed_allowed) {
+      const int n_tiles256 = static_cast<int>(a.N / 256);
+      const double cf = kb_total * kblock_cycles(256) + kTileFixedCycles, ch = kb_total * kblock_cycles(128) + kTileFixedCycles;
+      for (int nh = 2; nh <= 2 * n_tiles256; nh += 2) {
+        const int nf = n_tiles256 - nh / 2;
+        const long long full_items = mt * nf, all_items = mt * (nf + nh);
+        double worst = 0;
+        for (int pr = 0; pr < pairs && pr < all_items; ++pr) {
+          double c = 0;
+          for (long long w = pr; w < all_items; w += pairs) c += w < full_items ? cf : ch;
+          if (c > worst) worst = c;
+        }
+        if (worst < best - 1e-9) { best = worst; *bn_out = 256; *splits_out = 1; *n_half_out = nh; }
+      }
+    }
   }
 }
 
@@ -639,8 +696,8 @@ int gemm2_try_launch(const vitk_gemm_args& a, cudaStream_t stream, bool* handled
   const int sms = num_sms();
   // max_ctas leaves SMs free for a concurrent NCCL all-reduce (tile choice then balances waves over fewer pairs)
   const int pairs_avail = (a.max_ctas > 0 && a.max_ctas < sms ? a.max_ctas : sms) / 2;
-  int bn = 0, splits = 1;
-  choose_tiling2(a, pairs_avail, &bn, &splits);
+  int bn = 0, splits = 1, n_half = 0;
+  choose_tiling2(a, pairs_avail, &bn, &splits, &n_half);
   if (bn == 0) {
     VITK_REQUIRE(a.variant != 2, VITK_EINVAL, "gemm: no CTA-pair tiling for N=%lld tile_n=%d", (long long)a.N, a.tile_n);
     return 0;
@@ -648,7 +705,9 @@ int gemm2_try_launch(const vitk_gemm_args& a, cudaStream_t stream, bool* handled
   Gemm2Params p;
   p.M = static_cast<int>(a.M); p.N = static_cast<int>(a.N); p.K = static_cast<int>(a.K);
   const int m_tiles = (p.M + 2 * k2BM - 1) / (2 * k2BM);
-  p.n_tiles = p.N / bn;
+  p.n_half = n_half;
+  p.n_full = p.N / bn - n_half / 2;
+  p.n_tiles = p.n_full + p.n_half;
   p.mn_tiles = m_tiles * p.n_tiles;
   p.kb_total = (p.K + k2BK - 1) / k2BK;
   if (splits > p.kb_total) splits = p.kb_total;

@@ -170,3 +170,36 @@ def test_argument_errors(ops):
         ops.gemm(a, a, 128, 100, 64, d, epilogue=ops.EPI_STORE_F32)
     with pytest.raises(RuntimeError, match="split_k"):
         ops.gemm(a, a, 128, 128, 64, torch.zeros(128, 128, device=dev), epilogue=ops.EPI_STORE_F32, split_k=2)
+
+
+@pytest.mark.parametrize("b_mn", [False, True])
+@pytest.mark.parametrize("N,K", [(768, 192), (768, 768), (1280, 128)])
+def test_mixed_width_tiles_full_batch(ops, N, K, b_mn):
+    """M = 9232 (batch 16): 37 bands of 256 rows on 74 CTA pairs.  With N = 768 the pair kernel cuts every band into
+    2 tiles of 256 columns + 2 of 128 (one of each per pair) instead of 1.5 waves of 256-wide tiles; every epilogue
+    family has to cope with tiles of both widths in one launch (bias slices, aux look-ahead across a width change)."""
+    M = 9232
+    a, b, ref = _operands(M, N, K, False, b_mn, 21)
+    d = torch.full((M, N), float("nan"), device=dev, dtype=bf16)
+    ops.gemm(a, b, M, N, K, d, epilogue=ops.EPI_STORE_BF16, b_mn_major=b_mn)
+    assert (d.float() - ref).abs().max() <= _tol(K, ref) + 2 ** -8 * ref.abs().max()
+    pure = torch.empty_like(d)
+    ops.gemm(a, b, M, N, K, pure, epilogue=ops.EPI_STORE_BF16, b_mn_major=b_mn, tile_n=256 if N % 256 == 0 else 128)
+    assert torch.equal(d, pure)                      # same K order per element: the tiling must not change a bit
+    bias = torch.randn(N, device=dev)
+    res = torch.randn(M, N, device=dev)
+    out = res.clone()
+    ops.gemm(a, b, M, N, K, out, epilogue=ops.EPI_BIAS_RESID_F32, bias=bias, aux=out, b_mn_major=b_mn)
+    rr = ref + bias + res
+    assert (out - rr).abs().max() <= _tol(K, rr)
+    mult = (torch.randn(M, N, device=dev) * 0.5).to(bf16)
+    mul = torch.empty((M, N), device=dev, dtype=bf16)
+    ops.gemm(a, b, M, N, K, mul, epilogue=ops.EPI_MUL_BF16, aux=mult, b_mn_major=b_mn)
+    rm = ref * mult.float()
+    assert (mul.float() - rm).abs().max() <= _tol(K, rm) + 2 ** -8 * rm.abs().max()
+    act = torch.empty((M, N), device=dev, dtype=bf16)
+    gp = torch.empty((M, N), device=dev, dtype=bf16)
+    ops.gemm(a, b, M, N, K, act, epilogue=ops.EPI_BIAS_GELUG_BF16, d2=gp, bias=bias, b_mn_major=b_mn)
+    ur = ref + bias
+    gr = torch.nn.functional.gelu(ur)
+    assert (act.float() - gr).abs().max() <= _tol(K, ur) + 2 ** -8 * gr.abs().max()
