@@ -216,6 +216,9 @@ def instrumented_gemm_time(ar, plans, stream):
     run on); returns (Σ algorithmic FLOPs, Σ ms, launches) over all GEMM launches."""
     import torch
     tot_f, evs, n = 0.0, [], 0
+    torch.cuda.synchronize()
+    torch.cuda._sleep(4_000_000)   # ≈2 ms head start: the host enqueues ahead of the GPU, so each event pair brackets
+                                   # device time only (an idle GPU would add the host's launch latency to every interval)
     for plan in plans:
         fl = gemm_flops_of_plan(plan)
         for (fn, a, name), f in zip(plan.steps, fl):

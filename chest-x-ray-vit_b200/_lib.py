@@ -63,6 +63,7 @@ _PROTOS = {
     "vitk_clip_scale": (C.c_int, [_p, _f, _p, _p]),
     "vitk_launch_count": (C.c_int64, []),
     "vitk_debug_timeline": (C.c_int, [_p]),
+    "vitk_debug_stamp": (C.c_int, [C.c_int64, _p]),
 }
 
 _lib = None

@@ -390,7 +390,7 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __
 // masking (their dV/dK rows are never stored, their dQ contribution multiplies zero-filled K rows);
 // queries ≥ T have lse = +inf in the padded statistics, hence P = dS = 0.
 constexpr int kBwdComputeWarps = 16;
-constexpr int kBwdThreads = (kBwdComputeWarps + 1) * 32;
+constexpr int kBwdThreads = (kBwdComputeWarps + 2) * 32;   // 16 compute warps + MMA-issue warp + TMA-load warp
 constexpr int kQSub = 64;
 constexpr int kBwdSmemK = 0;
 constexpr int kBwdSmemV = kBwdSmemK + kTileBytes;
@@ -463,14 +463,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
     const uint64_t q_mnmaj = umma_smem_desc(smem_u32(sQ), kQSub * 128, 1024);
     const uint64_t do_mnmaj = umma_smem_desc(smem_u32(sDO), kQSub * 128, 1024);
     const uint64_t dst_mnmaj = umma_smem_desc(smem_u32(sDSt), kTileBytes, 1024);
-    auto load_qd = [&](int u) {              // sub-block u → ring slot u&3
-      const int slot = u & 3;
-      if (elect_one()) {
-        mbar_arrive_expect_tx(&bar_qd[slot], 2 * kQSub * 128);
-        tma_load_3d(sQ + slot * (kQSub * 128), &tma_q64, &bar_qd[slot], colq, u * kQSub, b);
-        tma_load_3d(sDO + slot * (kQSub * 128), &tma_do64, &bar_qd[slot], colq, u * kQSub, b);
-      }
-    };
     auto issue_scores = [&](int u) {
       const int x = u & 1;
       const uint64_t boff = static_cast<uint64_t>((u & 3) * kSub16);
@@ -485,12 +477,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
         tc_commit(&bar_s[x]);
       }
     };
-    if (elect_one()) {
-      mbar_arrive_expect_tx(bar_kv, 2 * kTileBytes);
-      tma_load_3d(sK, &tma_qkv, bar_kv, colk, key0, b);
-      tma_load_3d(sV, &tma_qkv, bar_kv, colv, key0, b);
-    }
-    for (int u = 0; u < 3 && u < nsub; ++u) load_qd(u);
     mbar_wait(bar_kv, 0);
     issue_scores(0);
     if (nsub > 1) issue_scores(1);
@@ -521,11 +507,30 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
       VITK_STAMP(16 * u + 1);
       if (u + 2 < nsub) issue_scores(u + 2);   // queued right behind: MMAs retire in issue order
       VITK_STAMP(16 * u + 2);
-      if (u + 3 < nsub) {                      // refill the ring slot of sub-block u−1: its dV/dK retired a step ago
-        if (u >= 1) mbar_wait(&bar_free[(u - 1) & 3], ((u - 1) >> 2) & 1);
-        load_qd(u + 3);
-      }
       VITK_STAMP(16 * u + 3);
+    }
+    __syncwarp();
+  } else if (warp == kBwdComputeWarps + 1) {
+    // ------------------------------------------------------------------ load warp: K/V once, then the Q/dO ring.
+    // (A separate warp: waiting here for a ring slot to be released — i.e. for dV/dK MMAs to retire — must not
+    // hold up the MMA-issue warp, which would stall the whole score → softmax → dV/dK chain of the other buffer.)
+    auto load_qd = [&](int u) {              // sub-block u → ring slot u&3
+      const int slot = u & 3;
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&bar_qd[slot], 2 * kQSub * 128);
+        tma_load_3d(sQ + slot * (kQSub * 128), &tma_q64, &bar_qd[slot], colq, u * kQSub, b);
+        tma_load_3d(sDO + slot * (kQSub * 128), &tma_do64, &bar_qd[slot], colq, u * kQSub, b);
+      }
+    };
+    if (elect_one()) {
+      mbar_arrive_expect_tx(bar_kv, 2 * kTileBytes);
+      tma_load_3d(sK, &tma_qkv, bar_kv, colk, key0, b);
+      tma_load_3d(sV, &tma_qkv, bar_kv, colv, key0, b);
+    }
+    for (int u = 0; u < 4 && u < nsub; ++u) load_qd(u);
+    for (int u = 4; u < nsub; ++u) {         // slot u&3 was last used by sub-block u−4: wait until its dV/dK retired
+      mbar_wait(&bar_free[u & 3], ((u - 4) >> 2) & 1);
+      load_qd(u);
     }
     __syncwarp();
   } else {
@@ -555,15 +560,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
         tma_store_commit();
       }
     };
+    // statistics of this warp's 16 queries (padded arrays: unconditional aligned loads), fetched one sub-block ahead
+    float4 l4[4], d4[4];
+#pragma unroll
+    for (int y = 0; y < 4; ++y) {
+      l4[y] = __ldg(reinterpret_cast<const float4*>(stat_lse) + y);
+      d4[y] = __ldg(reinterpret_cast<const float4*>(stat_dlt) + y);
+    }
     for (int u = 0; u < nsub; ++u) {
       const int i = u >> 1, hq = u & 1, x = u & 1;
-      // statistics of this warp's 16 queries (padded arrays: unconditional aligned loads), issued before the wait
-      float4 l4[4], d4[4];
-#pragma unroll
-      for (int y = 0; y < 4; ++y) {
-        l4[y] = __ldg(reinterpret_cast<const float4*>(stat_lse + u * kQSub) + y);
-        d4[y] = __ldg(reinterpret_cast<const float4*>(stat_dlt + u * kQSub) + y);
-      }
       if (warp == 0) VITK_STAMP(16 * u + 8);
       mbar_wait(&bar_s[x], (u >> 1) & 1);
       if (warp == 0) VITK_STAMP(16 * u + 9);
@@ -588,6 +593,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
         pk[2 * y + 1] = pack_bf16x2(p[2], p[3]);
         dk[2 * y] = pack_bf16x2(ds[0], ds[1]);
         dk[2 * y + 1] = pack_bf16x2(ds[2], ds[3]);
+      }
+      if (u + 1 < nsub) {           // next sub-block's statistics: in flight during the stores, fences and the next wait
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {
+          l4[y] = __ldg(reinterpret_cast<const float4*>(stat_lse + (u + 1) * kQSub) + y);
+          d4[y] = __ldg(reinterpret_cast<const float4*>(stat_dlt + (u + 1) * kQSub) + y);
+        }
       }
       if (warp == 0) VITK_STAMP(16 * u + 11);
       tmem_st_32x8(t_s, pk);        // Pᵀ  → this warp's own (consumed) Sᵀ columns: A operand of dV
@@ -713,6 +725,18 @@ extern "C" VITK_API int vitk_attn_fwd(const void* qkv, int64_t B, int64_t T, int
 
 extern "C" VITK_API int vitk_debug_timeline(void* device_buf) {
   g_timeline = static_cast<long long*>(device_buf);
+  return 0;
+}
+
+__global__ void debug_stamp_kernel(long long* dst) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  *dst = static_cast<long long>(t);
+}
+extern "C" VITK_API int vitk_debug_stamp(int64_t slot, void* stream) {
+  VITK_REQUIRE(g_timeline != nullptr && slot >= 0, VITK_EINVAL, "vitk_debug_stamp: no timeline buffer set");
+  debug_stamp_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(g_timeline + slot);
+  VITK_LAUNCH_CHECK("debug_stamp_kernel");
   return 0;
 }
 

@@ -76,7 +76,8 @@ struct Gemm2Params {
   const float* bias;
   long long* tl;      // vitk_debug_timeline buffer (nullptr in production): the leader CTA of pair 0 stamps clock64() per
                       // K block [4i]: producer passed the stage-empty wait, [4i+1]: MMA warp passed the stage-full wait,
-                      // [4i+2]: MMAs + commit issued; per tile [4096+4t]: epilogue warp 2 passed acc_full, [+1]: tile drained
+                      // [4i+2]: MMAs + commit issued; per tile [4096+4t]: epilogue warp 2 passed acc_full, [+1]: tile drained;
+                      // [6000+2c], [6001+2c]: globaltimer (ns) when CTA c starts working / has finished
 };
 extern long long* g_timeline;
 
@@ -165,6 +166,11 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   using Cfg = Cfg2<BN>;
   constexpr int kStages = Cfg::kStages;
   constexpr int kBHalf = Cfg::kBHalfRows;
+  if (p.tl != nullptr && threadIdx.x == 0) {   // debug timeline: [6400 + cta] = globaltimer at kernel entry
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.tl[6400 + blockIdx.x] = static_cast<long long>(t);
+  }
   extern __shared__ __align__(1024) uint8_t smem_raw[];   // 128-byte-swizzled operand tiles need 1024-byte alignment
   uint8_t* smem = smem_raw;
   uint8_t* staging = smem + kStages * Cfg::kStageBytes;
@@ -207,6 +213,11 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   pdl_wait();                  // the previous kernel's outputs are complete; everything above overlapped its tail
   pdl_launch_dependents();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // broadcast marks it warp-uniform: no per-MMA elect-broadcast-retry loop
+  if (p.tl != nullptr && threadIdx.x == 0) {   // debug timeline: [6000 + 2·cta] = globaltimer when this CTA starts working
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.tl[6000 + 2 * blockIdx.x] = static_cast<long long>(t);
+  }
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)
@@ -558,6 +569,11 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
 
   tc_fence_before_sync();
   __syncthreads();
+  if (p.tl != nullptr && threadIdx.x == 0) {   // [6001 + 2·cta] = globaltimer when all of this CTA's warps are done
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.tl[6001 + 2 * blockIdx.x] = static_cast<long long>(t);
+  }
   cluster_sync_all();   // neither CTA may free TMEM / exit while the peer can still reach it
   if (warp == 1) {
     tc_fence_after_sync();

@@ -184,9 +184,13 @@ VITK_API int vitk_clip_scale(const float* sumsq, float max_norm, float* scale, v
  * bf16 shadow refresh after optimizer.step(): dst_bf16[i] = bf16(src[i]). n multiple of 8. */
 VITK_API int vitk_cast_f32_bf16(const float* src, void* dst_bf16, int64_t n, vitk_stream_t stream);
 VITK_API int vitk_fill_zero(void* ptr, size_t bytes, vitk_stream_t stream);
-/* Diagnostics: when device_buf (>= 1024 int64) is non-NULL, CTA (0,0,0) of vitk_attn_bwd records clock64()
- * stamps of its pipeline phases into it (slot = 16·query_block + phase); NULL (default) disables. */
+/* Diagnostics: when device_buf is non-NULL, CTA (0,0,0) of vitk_attn_bwd records clock64() stamps of its pipeline
+ * phases into it (>= 1024 int64; slot = 16·query_block + phase) and the CTA-pair GEMM records per-K-block / per-tile /
+ * per-CTA stamps (>= 8192 int64; layout in csrc/gemm2.cu); NULL (default) disables. */
 VITK_API int vitk_debug_timeline(void* device_buf);
+/* Diagnostics: a one-thread kernel that writes %globaltimer (ns) to slot `slot` of the vitk_debug_timeline buffer, in
+ * stream order — brackets another launch with device-side time stamps. */
+VITK_API int vitk_debug_stamp(int64_t slot, vitk_stream_t stream);
 /* Number of kernels this library has launched in this process (all threads); bench.py reads it
  * around the timed region to report gpu_launches. */
 VITK_API int64_t vitk_launch_count(void);

@@ -22,15 +22,18 @@ dqkv = torch.empty(B * T, 3 * H * 64, dtype=torch.bfloat16, device=dev)
 def timeit(fn, reps=10):
     for _ in range(2):
         fn()
-    ts = []
+    torch.cuda.synchronize()
+    torch.cuda._sleep(2_000_000)      # host runs ahead of the GPU: the event pairs bracket device time only
+    evs = []
     for _ in range(reps):
         flush.fill_(1)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         fn()
         e1.record()
-        torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1))
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    ts = [a.elapsed_time(b) for a, b in evs]
     ts.sort()
     return ts[len(ts) // 2]
 

@@ -73,15 +73,20 @@ def run(c, reps=10, **kw):
     go = go or go_vitk
     for _ in range(2):
         go()
-    ts = []
+    # everything is enqueued behind a ~1 ms spin kernel so the host runs ahead of the GPU: the event pair then
+    # brackets device time only (with a sync per repetition the interval also contains ≈15–25 µs of host launch latency)
+    torch.cuda.synchronize()
+    torch.cuda._sleep(2_000_000)
+    evs = []
     for _ in range(reps):
         flush.fill_(1)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         go()
         e1.record()
-        torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1))
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    ts = [a.elapsed_time(b) for a, b in evs]
     ts.sort()
     return ts[len(ts) // 2]
 

@@ -31,10 +31,21 @@ def timeline(c, flush):
         bg.flush.fill_(1)
     torch.cuda.synchronize()
     lib.vitk_debug_timeline(tl.data_ptr())
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    cs = torch.cuda.current_stream().cuda_stream
+    torch.cuda._sleep(1_000_000)
+    if flush:
+        bg.flush.fill_(1)
+    lib.vitk_debug_stamp(7000, cs)
+    e0.record()
     go()
+    e1.record()
+    lib.vitk_debug_stamp(7001, cs)
     torch.cuda.synchronize()
     lib.vitk_debug_timeline(None)
-    return tl.cpu().tolist()
+    out = tl.cpu().tolist()
+    out.append(e0.elapsed_time(e1) * 1e3)
+    return out
 
 
 def report(c, flush):
@@ -46,6 +57,17 @@ def report(c, flush):
     E1 = [t[4096 + 4 * i + 1] for i in range(256) if t[4096 + 4 * i + 1]]
     n = min(len(P), len(F), len(I))
     t0 = P[0]
+    starts = [t[6000 + 2 * c] for c in range(148) if t[6000 + 2 * c]]
+    ends = [t[6001 + 2 * c] for c in range(148) if t[6001 + 2 * c]]
+    if starts and ends:
+        s0 = min(starts)
+        durs = sorted(e - s for s, e in zip(starts, ends))
+        print(f"   CTAs {len(starts)}: start spread {(max(starts) - s0) / 1e3:.1f} us, first start → last end {(max(ends) - s0) / 1e3:.1f} us, "
+              f"per-CTA busy min/median/max {durs[0] / 1e3:.1f}/{durs[len(durs) // 2] / 1e3:.1f}/{durs[-1] / 1e3:.1f} us, "
+              f"CTA 0 busy {(t[6001] - t[6000]) / 1e3:.1f} us; event time {t[-1]:.1f} us")
+        entries = [t[6400 + c] for c in range(148) if t[6400 + c]]
+        print(f"   device clock: stamp before → first CTA entry {(min(entries) - t[7000]) / 1e3:.1f} us, entry → start (prologue) "
+              f"{(s0 - min(entries)) / 1e3:.1f} us, last end → stamp after {(t[7001] - max(ends)) / 1e3:.1f} us, stamp to stamp {(t[7001] - t[7000]) / 1e3:.1f} us")
     print(f"=== {c['name'].strip()}  M={c['M']} N={c['N']} K={c['K']}  L2 {'flushed' if flush else 'warm'}: {n} K blocks, {len(E0)} tiles, "
           f"span {max(E1) - t0 if E1 else 0} cycles")
     kb_per_tile = n // max(len(E0), 1)
