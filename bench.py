@@ -414,7 +414,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="per-GPU batch (BASELINE configs[1]: 16)")
-    ap.add_argument("--layers-per-bucket", type=lambda v: [int(x) for x in v.split(",")], default=[3], help="encoder layers per all-reduce bucket (3 = 85 MB; best of 1/3/6/12 at N=4)")
+    ap.add_argument("--layers-per-bucket", type=lambda v: [int(x) for x in v.split(",")], default=[3, 3, 3, 2, 1], help="encoder layers per all-reduce bucket, in the order layers finish backward; last entry repeats (3 layers = 85 MB; tapered so the all-reduce left after backward is short)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
