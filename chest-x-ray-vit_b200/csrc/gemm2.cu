@@ -646,7 +646,10 @@ static int dispatch_major2(const vitk_gemm_args& a, const Gemm2Params& p, int pa
 // constant); split-K (wgrad only) multiplies the work items until one wave is full.
 // cycles a CTA pair spends per 64-wide K block of a tile of `bn` columns (tools/gemm_timeline.py, B200): the MMAs of a
 // 256-wide tile occupy the tensor pipe for 4 × 122 cycles; narrower tiles are bound by operand delivery instead
-static double kblock_cycles(int bn) { return bn == 256 ? 500.0 : (bn == 192 ? 440.0 : 390.0); }
+#ifndef VITK_K192
+#define VITK_K192 440.0   // A/B on the full step: 440 (192-wide tiles for K-major N = 768) beats 500 (mixed 256+128 there) by 0.9 %
+#endif
+static double kblock_cycles(int bn) { return bn == 256 ? 500.0 : (bn == 192 ? VITK_K192 : 390.0); }
 constexpr double kTileFixedCycles = 1500.0;   // accumulator hand-over + pipeline refill per tile
 
 static void choose_tiling2(const vitk_gemm_args& a, int pairs, int* bn_out, int* splits_out, int* n_half_out) {
