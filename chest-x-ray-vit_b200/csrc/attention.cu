@@ -22,11 +22,13 @@
 #include "common.cuh"
 #include "sm100_prims.cuh"
 #include "tmap.cuh"
+#include <stdlib.h>
 
 namespace vitk {
 
 // Optional per-phase timeline (vitk_debug_timeline): CTA (0,0,0) records clock64() stamps.
 long long* g_timeline = nullptr;   // also stamped by the CTA-pair GEMM (gemm2.cu)
+int g_timeline_seq = 0;            // GEMM launches since the buffer was set (per-launch min/max stamps)
 #define VITK_STAMP(slot)                                             \
   do {                                                               \
     if (tl != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0) tl[(slot)] = clock64(); \
@@ -725,6 +727,7 @@ extern "C" VITK_API int vitk_attn_fwd(const void* qkv, int64_t B, int64_t T, int
 
 extern "C" VITK_API int vitk_debug_timeline(void* device_buf) {
   g_timeline = static_cast<long long*>(device_buf);
+  g_timeline_seq = 0;
   return 0;
 }
 
@@ -735,6 +738,13 @@ __global__ void debug_stamp_kernel(long long* dst) {
 }
 extern "C" VITK_API int vitk_debug_stamp(int64_t slot, void* stream) {
   VITK_REQUIRE(g_timeline != nullptr && slot >= 0, VITK_EINVAL, "vitk_debug_stamp: no timeline buffer set");
+  static const int carve = [] {     // experiment: VITK_STAMP_CARVEOUT=100 keeps the SM in its max-shared-memory configuration
+    const char* e = getenv("VITK_STAMP_CARVEOUT");
+    const int c = e ? atoi(e) : -1;
+    if (c >= 0) cudaFuncSetAttribute(debug_stamp_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, c);
+    return c;
+  }();
+  (void)carve;
   debug_stamp_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(g_timeline + slot);
   VITK_LAUNCH_CHECK("debug_stamp_kernel");
   return 0;

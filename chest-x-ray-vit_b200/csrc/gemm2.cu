@@ -74,12 +74,15 @@ struct Gemm2Params {
   const void* aux;
   long long ld_aux;
   const float* bias;
+  int tl_seq;         // launch number since the timeline buffer was set: [7100 + 4·seq + {0,1,2,3}] = min entry, min start,
+                      // max end, max exit globaltimer over the CTAs of that launch (slots pre-set by the tool to ±inf)
   long long* tl;      // vitk_debug_timeline buffer (nullptr in production): the leader CTA of pair 0 stamps clock64() per
                       // K block [4i]: producer passed the stage-empty wait, [4i+1]: MMA warp passed the stage-full wait,
                       // [4i+2]: MMAs + commit issued; per tile [4096+4t]: epilogue warp 2 passed acc_full, [+1]: tile drained;
                       // [6000+2c], [6001+2c]: globaltimer (ns) when CTA c starts working / has finished
 };
 extern long long* g_timeline;
+extern int g_timeline_seq;
 
 struct Work2 {
   int m_blk, n0, bn, kb_begin, kb_end;   // n0: first output column, bn: tile width (BN or BN/2)
@@ -170,6 +173,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     p.tl[6400 + blockIdx.x] = static_cast<long long>(t);
+    if (p.tl_seq < 200) atomicMin(reinterpret_cast<unsigned long long*>(p.tl + 7100 + 4 * p.tl_seq), t);
   }
   extern __shared__ __align__(1024) uint8_t smem_raw[];   // 128-byte-swizzled operand tiles need 1024-byte alignment
   uint8_t* smem = smem_raw;
@@ -208,7 +212,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   if (warp == 1) tmem_alloc_pair(tmem_slot, Cfg::kTmemCols);
   tc_fence_before_sync();
   __syncthreads();
-  cluster_sync_all();          // peer barriers initialised, both TMEM allocations done
+  cluster_sync_relaxed();      // peer barriers initialised (fence.mbarrier_init above), both TMEM allocations done
   tc_fence_after_sync();
   pdl_wait();                  // the previous kernel's outputs are complete; everything above overlapped its tail
   pdl_launch_dependents();
@@ -217,6 +221,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     p.tl[6000 + 2 * blockIdx.x] = static_cast<long long>(t);
+    if (p.tl_seq < 200) atomicMin(reinterpret_cast<unsigned long long*>(p.tl + 7101 + 4 * p.tl_seq), t);
   }
 
   if (warp == 0) {
@@ -573,11 +578,18 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     p.tl[6001 + 2 * blockIdx.x] = static_cast<long long>(t);
+    if (p.tl_seq < 200) atomicMax(reinterpret_cast<unsigned long long*>(p.tl + 7102 + 4 * p.tl_seq), t);
   }
-  cluster_sync_all();   // neither CTA may free TMEM / exit while the peer can still reach it
+  cluster_sync_relaxed();   // neither CTA may free TMEM / exit while the peer can still reach it
   if (warp == 1) {
     tc_fence_after_sync();
     tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
+    if (p.tl != nullptr && lane == 0) {        // [6600 + cta] = globaltimer after the TMEM hand-back, right before exit
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      p.tl[6600 + blockIdx.x] = static_cast<long long>(t);
+      if (p.tl_seq < 200) atomicMax(reinterpret_cast<unsigned long long*>(p.tl + 7103 + 4 * p.tl_seq), t);
+    }
   }
 }
 
@@ -743,6 +755,7 @@ int gemm2_try_launch(const vitk_gemm_args& a, cudaStream_t stream, bool* handled
   p.ld_aux = a.ld_aux;
   p.bias = a.bias;
   p.tl = g_timeline;
+  p.tl_seq = g_timeline != nullptr ? g_timeline_seq++ : 0;
   const int pairs = p.total_work < pairs_avail ? p.total_work : pairs_avail;
   *handled = true;
   switch (bn) {

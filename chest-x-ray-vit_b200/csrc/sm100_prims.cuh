@@ -234,6 +234,14 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// Execution-only cluster barrier (what CUTLASS uses after barrier init): the default arrive.release compiles to
+// MEMBAR.ALL.GPU + L1 invalidation and, at the end of a kernel that has just written tens of MB, costs microseconds.
+// Callers order what they need themselves (fence.mbarrier_init before it in the prologue; at teardown every remote
+// mbarrier arrive was issued long before and all bulk stores have been waited for).
+__device__ __forceinline__ void cluster_sync_relaxed() {
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
+}
 // shared::cta address of this CTA → shared::cluster address of the same offset in CTA `rank`
 __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
   uint32_t r;

@@ -41,11 +41,47 @@ def timeline(c, flush):
     go()
     e1.record()
     lib.vitk_debug_stamp(7001, cs)
+    lib.vitk_debug_stamp(7002, cs)     # back-to-back stamps: the launch-to-launch gap of trivial kernels
+    lib.vitk_debug_stamp(7003, cs)
     torch.cuda.synchronize()
     lib.vitk_debug_timeline(None)
     out = tl.cpu().tolist()
     out.append(e0.elapsed_time(e1) * 1e3)
     return out
+
+
+def chain(c, n=10):
+    """n identical launches back to back (PDL chain, like the training step): where the device time of a launch goes."""
+    tl = torch.zeros(8192, dtype=torch.int64, device="cuda")
+    big = torch.iinfo(torch.int64).max
+    for i in range(n + 1):
+        tl[7100 + 4 * i] = big
+        tl[7101 + 4 * i] = big
+
+    def go():
+        ops.gemm(c["a"], c["b"], c["M"], c["N"], c["K"], c["d"], epilogue=c["epi"], a_mn_major=c["a_mn"], b_mn_major=c["b_mn"],
+                 **c["extra"], **KW)
+    go()
+    torch.cuda.synchronize()
+    lib.vitk_debug_timeline(tl.data_ptr())
+    cs = torch.cuda.current_stream().cuda_stream
+    torch.cuda._sleep(1_000_000)
+    lib.vitk_debug_stamp(7000, cs)
+    for _ in range(n):
+        go()
+    lib.vitk_debug_stamp(7001, cs)
+    torch.cuda.synchronize()
+    lib.vitk_debug_timeline(None)
+    t = tl.cpu().tolist()
+    L = [(t[7100 + 4 * i], t[7101 + 4 * i], t[7102 + 4 * i], t[7103 + 4 * i]) for i in range(n)]
+    per = (t[7001] - t[7000]) / 1e3 / n
+    mid = L[2:-1]
+    gap = sum(L[i][0] - L[i - 1][3] for i in range(3, n - 1)) / max(len(mid) - 1, 1) / 1e3
+    pro = sum(x[1] - x[0] for x in mid) / len(mid) / 1e3
+    busy = sum(x[2] - x[1] for x in mid) / len(mid) / 1e3
+    tear = sum(x[3] - x[2] for x in mid) / len(mid) / 1e3
+    print(f"=== {c['name'].strip()}: {n} launches back to back: {per:.1f} us per launch = previous kernel's last exit → first CTA entry {gap:.1f}"
+          f" + entry → work start (prologue, dependency wait) {pro:.1f} + work {busy:.1f} + work end → last exit {tear:.1f} us")
 
 
 def report(c, flush):
@@ -65,9 +101,13 @@ def report(c, flush):
         print(f"   CTAs {len(starts)}: start spread {(max(starts) - s0) / 1e3:.1f} us, first start → last end {(max(ends) - s0) / 1e3:.1f} us, "
               f"per-CTA busy min/median/max {durs[0] / 1e3:.1f}/{durs[len(durs) // 2] / 1e3:.1f}/{durs[-1] / 1e3:.1f} us, "
               f"CTA 0 busy {(t[6001] - t[6000]) / 1e3:.1f} us; event time {t[-1]:.1f} us")
+        exits = [t[6600 + c] for c in range(148) if t[6600 + c]]
+        if exits:
+            print(f"   last CTA work end → last TMEM hand-back (just before exit) {(max(exits) - max(ends)) / 1e3:.2f} us; that → next kernel's stamp {(t[7001] - max(exits)) / 1e3:.2f} us")
         entries = [t[6400 + c] for c in range(148) if t[6400 + c]]
         print(f"   device clock: stamp before → first CTA entry {(min(entries) - t[7000]) / 1e3:.1f} us, entry → start (prologue) "
-              f"{(s0 - min(entries)) / 1e3:.1f} us, last end → stamp after {(t[7001] - max(ends)) / 1e3:.1f} us, stamp to stamp {(t[7001] - t[7000]) / 1e3:.1f} us")
+              f"{(s0 - min(entries)) / 1e3:.1f} us, last end → stamp after {(t[7001] - max(ends)) / 1e3:.1f} us, stamp to stamp {(t[7001] - t[7000]) / 1e3:.1f} us "
+              f"(trivial kernel → trivial kernel: {(t[7002] - t[7001]) / 1e3:.1f}, {(t[7003] - t[7002]) / 1e3:.1f} us)")
     print(f"=== {c['name'].strip()}  M={c['M']} N={c['N']} K={c['K']}  L2 {'flushed' if flush else 'warm'}: {n} K blocks, {len(E0)} tiles, "
           f"span {max(E1) - t0 if E1 else 0} cycles")
     kb_per_tile = n // max(len(E0), 1)
@@ -95,6 +135,9 @@ def report(c, flush):
 sel = [a for a in argv if not a.startswith("-")]
 for c in bg.CASES:
     if sel and not any(s in c["name"] for s in sel):
+        continue
+    if "--chain" in argv:
+        chain(c)
         continue
     for flush in (True, False):
         report(c, flush)
