@@ -289,6 +289,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       int acc = 0;
       uint32_t acc_phase = 0;
       int kbi = 0;
+      int tiles_done = 0;
       for (int w = pair_id; w < p.total_work; w += num_pairs) {
         const Work2 it = decode_work2<BN>(p, w);
         const int kb_begin = it.kb_begin, kb_end = it.kb_end;
@@ -321,6 +322,15 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
         }
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
+        ++tiles_done;
+      }
+      // Teardown guard: the peer CTA's epilogue warps release accumulators with REMOTE arrives on this CTA's
+      // acc_empty barriers.  Wait until the last release of each buffer has landed, so that no arrive can still be
+      // in flight towards this CTA's shared memory when it exits (the final cluster barrier is execution-only).
+#pragma unroll
+      for (int bsel = 0; bsel < 2; ++bsel) {
+        const int uses = (tiles_done + 1 - bsel) >> 1;          // tiles that used accumulator buffer bsel
+        if (uses > 0) mbar_wait(&acc_empty[bsel], (uses - 1) & 1);
       }
     }
     __syncwarp();
@@ -514,10 +524,13 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
           case VITK_EPI_BIAS_GELUG_BF16: {     // d = gelu(u), d2 = gelu'(u) (optional)
             float g2[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const GeluParts g = gelu_parts(v[i]);
-              g2[i] = fmaf(v[i], g.pdf, g.cdf);
-              v[i] *= g.cdf;
+            for (int i = 0; i < 32; i += 2) {
+              const float2 u2 = make_float2(v[i], v[i + 1]);
+              const GeluParts2 g = gelu_parts2(u2);
+              const float2 d = __ffma2_rn(u2, g.pdf, g.cdf);
+              const float2 a = __fmul2_rn(u2, g.cdf);
+              g2[i] = d.x; g2[i + 1] = d.y;
+              v[i] = a.x; v[i + 1] = a.y;
             }
             pack4(v, q);
             emit(&tma_d, col, row0, q);
