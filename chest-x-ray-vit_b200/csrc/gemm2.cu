@@ -160,16 +160,26 @@ __device__ __forceinline__ void add_bias32(const float* __restrict__ bias, int c
   }
 }
 
-template <int BN, bool A_MN, bool B_MN>
+// AUX: instantiation for the epilogues that read a residual / multiplier tile (BIAS_RESID_F32, MUL_BF16, DGELU_BF16).
+// Two instantiations because the epilogue sits at the 168-register cap (10 warps, 3 per SM sub-partition): the
+// aux look-ahead registers and the GELU temporaries never coexist, and with both in one kernel ptxas spilled the
+// prefetched bias across the accumulator wait — i.e. stalled on that load once per tile.
+template <int BN, bool A_MN, bool B_MN, bool AUX>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                   const __grid_constant__ CUtensorMap tma_bh,   // K-major B, box of BN/4 rows (half-width tiles)
                   const __grid_constant__ CUtensorMap tma_d, const __grid_constant__ CUtensorMap tma_d2,
                   const Gemm2Params p) {
+  // Timeline stamps are compiled in only for the diagnostic build (tools/build_variants.sh stamps "-DVITK_GEMM_STAMPS=1",
+  // selected with VITK_LIB): in the production kernel they would cost registers the epilogue does not have.
+#ifndef VITK_GEMM_STAMPS
+#define VITK_GEMM_STAMPS 0
+#endif
+  constexpr bool kStamps = VITK_GEMM_STAMPS != 0;
   using Cfg = Cfg2<BN>;
   constexpr int kStages = Cfg::kStages;
   constexpr int kBHalf = Cfg::kBHalfRows;
-  if (p.tl != nullptr && threadIdx.x == 0) {   // debug timeline: [6400 + cta] = globaltimer at kernel entry
+  if (kStamps && p.tl != nullptr && threadIdx.x == 0) {   // debug timeline: [6400 + cta] = globaltimer at kernel entry
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     p.tl[6400 + blockIdx.x] = static_cast<long long>(t);
@@ -193,7 +203,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   const bool leader = cta_rank == 0;
   const int pair_id = blockIdx.x >> 1;
   const int num_pairs = gridDim.x >> 1;
-  const bool stamp = p.tl != nullptr && blockIdx.x == 0;
+  const bool stamp = kStamps && p.tl != nullptr && blockIdx.x == 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
@@ -217,7 +227,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   pdl_wait();                  // the previous kernel's outputs are complete; everything above overlapped its tail
   pdl_launch_dependents();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // broadcast marks it warp-uniform: no per-MMA elect-broadcast-retry loop
-  if (p.tl != nullptr && threadIdx.x == 0) {   // debug timeline: [6000 + 2·cta] = globaltimer when this CTA starts working
+  if (kStamps && p.tl != nullptr && threadIdx.x == 0) {   // debug timeline: [6000 + 2·cta] = globaltimer when this CTA starts working
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     p.tl[6000 + 2 * blockIdx.x] = static_cast<long long>(t);
@@ -348,7 +358,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     float* bias_base = reinterpret_cast<float*>(staging + k2StagingBytes) + col_half * 256;   // [tile parity][128], shared by the 4 warps of this column half
     const int epi = p.epi;
     const bool out_f32 = epi == VITK_EPI_BIAS_RESID_F32 || epi == VITK_EPI_ACCUM_F32 || epi == VITK_EPI_STORE_F32;
-    const bool has_aux = !(p.dbg & 2) && (epi == VITK_EPI_BIAS_RESID_F32 || epi == VITK_EPI_MUL_BF16 || epi == VITK_EPI_DGELU_BF16);
+    const bool has_aux = AUX && !(p.dbg & 2) && (epi == VITK_EPI_BIAS_RESID_F32 || epi == VITK_EPI_MUL_BF16 || epi == VITK_EPI_DGELU_BF16);
     const bool has_bias = p.bias != nullptr && (epi == VITK_EPI_BIAS_BF16 || epi == VITK_EPI_BIAS_GELU_BF16 ||
                                                 epi == VITK_EPI_BIAS_GELUG_BF16 || epi == VITK_EPI_BIAS_RESID_F32);
     const int cw = out_f32 ? 16 : 32;                      // chunk width in columns
@@ -514,6 +524,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
             emit(&tma_d, col, row0, q);
             break;
           case VITK_EPI_BIAS_GELU_BF16:        // d = u, d2 = gelu(u)
+            if constexpr (AUX) break;
             pack4(v, q);
             emit(&tma_d, col, row0, q);
 #pragma unroll
@@ -522,26 +533,31 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
             emit(&tma_d2, col, row0, q);
             break;
           case VITK_EPI_BIAS_GELUG_BF16: {     // d = gelu(u), d2 = gelu'(u) (optional)
-            float g2[32];
+            if constexpr (AUX) break;
+            // packed as produced (two results → one bf16x2 word each), so only the packed outputs stay live
+            uint4 qg[4];
 #pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              const float2 u2 = make_float2(v[i], v[i + 1]);
-              const GeluParts2 g = gelu_parts2(u2);
-              const float2 d = __ffma2_rn(u2, g.pdf, g.cdf);
-              const float2 a = __fmul2_rn(u2, g.cdf);
-              g2[i] = d.x; g2[i + 1] = d.y;
-              v[i] = a.x; v[i + 1] = a.y;
+            for (int j = 0; j < 4; ++j) {
+              uint32_t wa[4], wg[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 u2 = make_float2(v[8 * j + 2 * i], v[8 * j + 2 * i + 1]);
+                const GeluParts2 g = gelu_parts2(u2);
+                const float2 d = __ffma2_rn(u2, g.pdf, g.cdf);
+                const float2 a = __fmul2_rn(u2, g.cdf);
+                wa[i] = pack_bf16x2(a.x, a.y);
+                wg[i] = pack_bf16x2(d.x, d.y);
+              }
+              q[j] = make_uint4(wa[0], wa[1], wa[2], wa[3]);
+              qg[j] = make_uint4(wg[0], wg[1], wg[2], wg[3]);
             }
-            pack4(v, q);
             emit(&tma_d, col, row0, q);
-            if (p.has_d2) {
-              pack4(g2, q);
-              emit(&tma_d2, col, row0, q);
-            }
+            if (p.has_d2) emit(&tma_d2, col, row0, qg);
             break;
           }
           case VITK_EPI_MUL_BF16:
           case VITK_EPI_DGELU_BF16: {
+            if constexpr (!AUX) break;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const uint32_t wv[4] = {arow[j].x, arow[j].y, arow[j].z, arow[j].w};
@@ -557,6 +573,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
             break;
           }
           case VITK_EPI_BIAS_RESID_F32:
+            if constexpr (!AUX) break;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               q[j].x = __float_as_uint(v[4 * j] + __uint_as_float(arow[j].x));
@@ -587,7 +604,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
 
   tc_fence_before_sync();
   __syncthreads();
-  if (p.tl != nullptr && threadIdx.x == 0) {   // [6001 + 2·cta] = globaltimer when all of this CTA's warps are done
+  if (kStamps && p.tl != nullptr && threadIdx.x == 0) {   // [6001 + 2·cta] = globaltimer when all of this CTA's warps are done
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     p.tl[6001 + 2 * blockIdx.x] = static_cast<long long>(t);
@@ -597,7 +614,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   if (warp == 1) {
     tc_fence_after_sync();
     tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
-    if (p.tl != nullptr && lane == 0) {        // [6600 + cta] = globaltimer after the TMEM hand-back, right before exit
+    if (kStamps && p.tl != nullptr && lane == 0) {        // [6600 + cta] = globaltimer after the TMEM hand-back, right before exit
       unsigned long long t;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
       p.tl[6600 + blockIdx.x] = static_cast<long long>(t);
@@ -615,7 +632,7 @@ static int out_map(CUtensorMap* m, const void* base, bool f32, long long rows, l
   return get_tensor_map(m, base, f32 ? TM_F32 : TM_BF16, 2, dims, str, box, TM_SW64);
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, bool AUX>
 static int launch_gemm2(const vitk_gemm_args& a, const Gemm2Params& p, int pairs, cudaStream_t stream) {
   using Cfg = Cfg2<BN>;
   CUtensorMap ta, tb, tbh, td, td2;
@@ -640,7 +657,7 @@ static int launch_gemm2(const vitk_gemm_args& a, const Gemm2Params& p, int pairs
   if (int rc = out_map(&td, a.d, f32_out, a.M, a.N, a.ldd)) return rc;
   td2 = td;
   if (a.d2 != nullptr) { if (int rc = out_map(&td2, a.d2, false, a.M, a.N, a.ldd)) return rc; }
-  auto kern = gemm2_bf16_kernel<BN, A_MN, B_MN>;
+  auto kern = gemm2_bf16_kernel<BN, A_MN, B_MN, AUX>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [&] {
@@ -653,22 +670,20 @@ static int launch_gemm2(const vitk_gemm_args& a, const Gemm2Params& p, int pairs
   return 0;
 }
 
-template <int BN>
+template <int BN, bool AUX>
 static int dispatch_major2(const vitk_gemm_args& a, const Gemm2Params& p, int pairs, cudaStream_t s) {
-  if (!a.a_mn_major && !a.b_mn_major) return launch_gemm2<BN, false, false>(a, p, pairs, s);
-  if (a.a_mn_major && !a.b_mn_major) return launch_gemm2<BN, true, false>(a, p, pairs, s);
-  if constexpr (BN != 192) {     // an MN-major B half must be whole 64-column TMA boxes
-    if (!a.a_mn_major && a.b_mn_major) return launch_gemm2<BN, false, true>(a, p, pairs, s);
-    return launch_gemm2<BN, true, true>(a, p, pairs, s);
+  if (!a.a_mn_major && !a.b_mn_major) return launch_gemm2<BN, false, false, AUX>(a, p, pairs, s);
+  if constexpr (!AUX) {          // wgrad layouts (MN-major A) never carry an aux tile
+    if (a.a_mn_major && !a.b_mn_major) return launch_gemm2<BN, true, false, false>(a, p, pairs, s);
   }
-  return set_error(VITK_EINVAL, "gemm2: tile_n 192 needs a K-major B operand");
+  if constexpr (BN != 192) {     // an MN-major B half must be whole 64-column TMA boxes
+    if (!a.a_mn_major && a.b_mn_major) return launch_gemm2<BN, false, true, AUX>(a, p, pairs, s);
+    if constexpr (!AUX) return launch_gemm2<BN, true, true, false>(a, p, pairs, s);
+  }
+  return set_error(VITK_EINVAL, "gemm2: unsupported operand layout for this tile width / epilogue (tile_n 192 needs a K-major B; "
+                                "aux epilogues need a K-major A)");
 }
 
-// Tile choice.  Per 64-wide K block a CTA pair needs max(MMA time, shared-memory time): the MMAs take
-// 2·BN cycles, and shared memory (128 B/clk per SM) has to absorb the TMA fill and the UMMA operand
-// reads of (16 KB of A + 64·BN bytes of B) per CTA — 512 / 448 / 384 cycles for BN = 256 / 192 / 128, so
-// narrow tiles are shared-memory-bound.  cost = waves × (K blocks × that + a per-tile fill/epilogue
-// constant); split-K (wgrad only) multiplies the work items until one wave is full.
 // cycles a CTA pair spends per 64-wide K block of a tile of `bn` columns (tools/gemm_timeline.py, B200): the MMAs of a
 // 256-wide tile occupy the tensor pipe for 4 × 122 cycles; narrower tiles are bound by operand delivery instead
 #ifndef VITK_K192
@@ -729,7 +744,9 @@ static void choose_tiling2(const vitk_gemm_args& a, int pairs, int* bn_out, int*
 int gemm2_try_launch(const vitk_gemm_args& a, cudaStream_t stream, bool* handled) {
   *handled = false;
   if (a.variant == 1) return 0;
+  const bool aux_epi = a.epilogue == VITK_EPI_BIAS_RESID_F32 || a.epilogue == VITK_EPI_MUL_BF16 || a.epilogue == VITK_EPI_DGELU_BF16;
   const bool eligible = a.epilogue != VITK_EPI_PATCH_F32 && a.N % 128 == 0 && (a.max_ctas == 0 || a.max_ctas >= 2) &&
+                        !(aux_epi && a.a_mn_major) &&     // the aux instantiations exist for K-major A only
                         (a.tile_n == 0 || a.tile_n == 128 || a.tile_n == 192 || a.tile_n == 256) &&
                         !(a.tile_n == 192 && a.b_mn_major);
   if (!eligible) {
@@ -772,9 +789,9 @@ int gemm2_try_launch(const vitk_gemm_args& a, cudaStream_t stream, bool* handled
   const int pairs = p.total_work < pairs_avail ? p.total_work : pairs_avail;
   *handled = true;
   switch (bn) {
-    case 256: return dispatch_major2<256>(a, p, pairs, stream);
-    case 192: return dispatch_major2<192>(a, p, pairs, stream);
-    default: return dispatch_major2<128>(a, p, pairs, stream);
+    case 256: return aux_epi ? dispatch_major2<256, true>(a, p, pairs, stream) : dispatch_major2<256, false>(a, p, pairs, stream);
+    case 192: return aux_epi ? dispatch_major2<192, true>(a, p, pairs, stream) : dispatch_major2<192, false>(a, p, pairs, stream);
+    default: return aux_epi ? dispatch_major2<128, true>(a, p, pairs, stream) : dispatch_major2<128, false>(a, p, pairs, stream);
   }
 }
 

@@ -7,6 +7,12 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+# the stamps are compiled out of the production library: use the diagnostic build (tools/build_variants.sh stamps "-DVITK_GEMM_STAMPS=1")
+_stamps = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "chest-x-ray-vit_b200", "csrc", "build", "variants", "libvitk_stamps.so")
+if "VITK_LIB" not in os.environ:
+    if not os.path.exists(_stamps):
+        sys.exit("build the diagnostic library first: tools/build_variants.sh stamps \"-DVITK_GEMM_STAMPS=1\"")
+    os.environ["VITK_LIB"] = os.path.abspath(_stamps)
 sys.argv, argv = sys.argv[:1] + ["--none"], sys.argv[1:]
 import bench_gemm as bg  # noqa: E402  (builds CASES; "--none" keeps it from running its table)
 
