@@ -241,6 +241,32 @@ def instrumented_gemm_time(ar, plans, stream):
     return tot_f, sum(a.elapsed_time(b) for a, b in evs), n
 
 
+def gemm_chain_time(plans, stream, reps=3):
+    """All GEMM launches of the plans back to back on the launch stream (programmatic-dependent-launch chain intact, as
+    in the step) inside ONE CUDA-event pair; returns (Σ algorithmic FLOPs, best ms, launches).  The buffers hold a real
+    step's data, so shapes, epilogues and memory footprints are the step's own."""
+    import torch
+    calls, tot_f = [], 0.0
+    for plan in plans:
+        for (fn, a, name), f in zip(plan.steps, gemm_flops_of_plan(plan)):
+            if fn is not None and f is not None:
+                calls.append((fn, a))
+                tot_f += f
+    best = float("inf")
+    for _ in range(reps):
+        torch.cuda.synchronize()
+        torch.cuda._sleep(4_000_000)      # head start: the host enqueues ahead of the GPU
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for fn, a in calls:
+            rc = fn(*a, stream)
+            assert rc == 0
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    return tot_f, best, len(calls)
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -374,10 +400,16 @@ def run_ours(args):
         pkg.ops.patchify_f32(x_dev[0], out=ar.apatch)
         for _ in range(2):
             flops, gms, n = instrumented_gemm_time(ar, [ar.fwd_loss, ar.bwd_loss], stream)
-        achieved = flops / (gms / 1e3) / 1e12
-        roof = {"bound": "tensor", "kernel": "gemm_bf16_kernel (all forward/dgrad/wgrad launches of one step)",
+        per_launch = flops / (gms / 1e3) / 1e12
+        cflops, cms, cn = gemm_chain_time([ar.fwd_loss, ar.bwd_loss], stream)
+        achieved = cflops / (cms / 1e3) / 1e12
+        roof = {"bound": "tensor", "kernel": "gemm2_bf16_kernel / gemm_bf16_kernel (all forward/dgrad/wgrad launches of one step)",
                 "achieved": achieved, "peak": pk["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tflops_sustained"],
-                "traffic": measured_traffic(), "launches_per_step": n, "gemm_ms_per_step": gms, "peak_source": pk["src"] + " (sustained)",
+                "traffic": measured_traffic(), "launches_per_step": cn, "gemm_ms_per_step": cms,
+                "how": "one CUDA-event pair around the step's GEMM launches issued back to back on the launch stream "
+                       "(average launch duration = that time / launches)",
+                "achieved_event_pair_per_launch": per_launch, "gemm_ms_per_step_event_pair_per_launch": gms,
+                "peak_source": pk["src"] + " (sustained)",
                 "step_tensor_frac": value / world * TRAIN_GF_PER_IMG / 1e3 / pk["tflops_sustained"]}
     if world > 1:
         dist.barrier()
