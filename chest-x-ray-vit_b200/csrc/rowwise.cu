@@ -290,12 +290,20 @@ __global__ void __launch_bounds__(128) embed_bwd_kernel(const __nv_bfloat16* __r
   const int t = blockIdx.x;
   for (int c8 = threadIdx.x; c8 < D / 8; c8 += blockDim.x) {
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int b = 0; b < B; ++b) {
-      const uint4 q = __ldg(reinterpret_cast<const uint4*>(dh + (static_cast<long long>(b) * T + t) * D) + c8);
-      if (t > 0) reinterpret_cast<uint4*>(dpatch + (static_cast<long long>(b) * (T - 1) + (t - 1)) * D)[c8] = q;
-      const float2 a = unbf2(q.x), bb = unbf2(q.y), c = unbf2(q.z), d = unbf2(q.w);
-      acc[0] += a.x; acc[1] += a.y; acc[2] += bb.x; acc[3] += bb.y;
-      acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
+    for (int b0 = 0; b0 < B; b0 += 8) {          // 8 images' loads in flight per thread (a serial loop paid one memory latency per image)
+      uint4 q[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        q[j] = (b0 + j < B) ? __ldg(reinterpret_cast<const uint4*>(dh + (static_cast<long long>(b0 + j) * T + t) * D) + c8)
+                            : make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (b0 + j >= B) break;
+        if (t > 0) reinterpret_cast<uint4*>(dpatch + (static_cast<long long>(b0 + j) * (T - 1) + (t - 1)) * D)[c8] = q[j];
+        const float2 a = unbf2(q[j].x), bb = unbf2(q[j].y), c = unbf2(q[j].z), d = unbf2(q[j].w);
+        acc[0] += a.x; acc[1] += a.y; acc[2] += bb.x; acc[3] += bb.y;
+        acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
+      }
     }
     float* pp = dpos + static_cast<long long>(t) * D + c8 * 8;
 #pragma unroll
