@@ -283,38 +283,45 @@ __global__ void embed_cls_kernel(const float* __restrict__ cls, const float* __r
   h[static_cast<long long>(b) * T * D + d] = cls[d] + pos[d];
 }
 
-// block = token t; thread = 8 columns.  dpos[t] += Σ_b dh[b,t]; t=0 → dcls; t≥1 → dbias, dpatch copy.
+// thread = 8 columns; a block walks tokens t = blockIdx.x, blockIdx.x + gridDim.x, …  dpos[t] += Σ_b dh[b,t]; t=0 → dcls;
+// t≥1 → dbias, dpatch copy.  The bias partials stay in registers across the block's tokens, so dbias sees one atomic
+// per column per BLOCK — with one block per token 576 atomics piled up on each of only 768 addresses (24 cache
+// lines) and that serialisation was most of the kernel's 51 µs.
 __global__ void __launch_bounds__(128) embed_bwd_kernel(const __nv_bfloat16* __restrict__ dh, int B, int T, int D,
                                                         float* __restrict__ dpos, float* __restrict__ dcls,
                                                         float* __restrict__ dbias, __nv_bfloat16* __restrict__ dpatch) {
-  const int t = blockIdx.x;
   for (int c8 = threadIdx.x; c8 < D / 8; c8 += blockDim.x) {
-    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int b0 = 0; b0 < B; b0 += 8) {          // 8 images' loads in flight per thread (a serial loop paid one memory latency per image)
-      uint4 q[8];
+    float bias_acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int t = blockIdx.x; t < T; t += gridDim.x) {
+      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int b0 = 0; b0 < B; b0 += 8) {          // 8 images' loads in flight per thread
+        uint4 q[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        q[j] = (b0 + j < B) ? __ldg(reinterpret_cast<const uint4*>(dh + (static_cast<long long>(b0 + j) * T + t) * D) + c8)
-                            : make_uint4(0, 0, 0, 0);
+        for (int j = 0; j < 8; ++j)
+          q[j] = (b0 + j < B) ? __ldg(reinterpret_cast<const uint4*>(dh + (static_cast<long long>(b0 + j) * T + t) * D) + c8)
+                              : make_uint4(0, 0, 0, 0);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (b0 + j >= B) break;
-        if (t > 0) reinterpret_cast<uint4*>(dpatch + (static_cast<long long>(b0 + j) * (T - 1) + (t - 1)) * D)[c8] = q[j];
-        const float2 a = unbf2(q[j].x), bb = unbf2(q[j].y), c = unbf2(q[j].z), d = unbf2(q[j].w);
-        acc[0] += a.x; acc[1] += a.y; acc[2] += bb.x; acc[3] += bb.y;
-        acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
+        for (int j = 0; j < 8; ++j) {
+          if (b0 + j >= B) break;
+          if (t > 0) reinterpret_cast<uint4*>(dpatch + (static_cast<long long>(b0 + j) * (T - 1) + (t - 1)) * D)[c8] = q[j];
+          const float2 a = unbf2(q[j].x), bb = unbf2(q[j].y), c = unbf2(q[j].z), d = unbf2(q[j].w);
+          acc[0] += a.x; acc[1] += a.y; acc[2] += bb.x; acc[3] += bb.y;
+          acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
+        }
+      }
+      float* pp = dpos + static_cast<long long>(t) * D + c8 * 8;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) pp[i] += acc[i];  // (t, column) has exactly one owner
+      if (t == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dcls[c8 * 8 + i] += acc[i];
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) bias_acc[i] += acc[i];
       }
     }
-    float* pp = dpos + static_cast<long long>(t) * D + c8 * 8;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) pp[i] += acc[i];  // (t, column) has exactly one owner
-    if (t == 0) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) dcls[c8 * 8 + i] += acc[i];
-    } else {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) atomicAdd(dbias + c8 * 8 + i, acc[i]);
-    }
+    for (int i = 0; i < 8; ++i) atomicAdd(dbias + c8 * 8 + i, bias_acc[i]);
   }
 }
 
@@ -465,7 +472,8 @@ extern "C" VITK_API int vitk_embed_bwd(const void* dh, int64_t B, int64_t T, int
                               void* dpatch, vitk_stream_t stream) {
   VITK_REQUIRE(dh && dpos && dcls && dbias && dpatch && B > 0 && T > 1, VITK_EINVAL, "embed_bwd: bad argument");
   VITK_REQUIRE(D % 8 == 0 && aligned16(dh) && aligned16(dpatch), VITK_EALIGN, "embed_bwd: alignment");
-  embed_bwd_kernel<<<static_cast<unsigned>(T), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+  const unsigned grid = static_cast<unsigned>(T < num_sms() ? T : num_sms());
+  embed_bwd_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(dh), (int)B, (int)T, (int)D, dpos, dcls, dbias, static_cast<__nv_bfloat16*>(dpatch));
   VITK_LAUNCH_CHECK("embed_bwd_kernel");
   return 0;
