@@ -1,23 +1,32 @@
 // CTA-pair (cta_group::2) persistent bf16 GEMM for sm_100a — the main dense-contraction kernel.
 //
 // One cluster of two CTAs (two SMs of a TPC) owns a 256×BN output tile: each CTA stages its own
-// 128 rows of A and HALF of the B tile (BN/2 rows) with TMA, the leader CTA's single MMA thread
-// issues tcgen05.mma.cta_group::2 (M = 256) which reads both CTAs' shared memory, and each CTA
-// ends up with its 128 accumulator rows in its own TMEM.  Compared with the single-CTA kernel in
-// gemm.cu this halves the B traffic from L2 and the B reads from shared memory per FLOP.
+// 128 rows of A and HALF of the B tile (BN/2 rows) with TMA, the leader CTA issues
+// tcgen05.mma.cta_group::2 (M = 256) which reads both CTAs' shared memory, and each CTA ends up with
+// its 128 accumulator rows in its own TMEM.  Compared with the single-CTA kernel in gemm.cu this
+// halves the B traffic from L2 and the B reads from shared memory per FLOP.
 //
-//   warp 0        TMA producer (lane 0): A half + B half per 64-wide K block into a ring of stages;
-//                 both CTAs' loads complete on the LEADER's full barrier
-//   warp 1        TMEM allocation (both CTAs); in the leader, lane 0 issues the MMAs and commits to
-//                 the stage-empty barriers (multicast to both CTAs) and the accumulator-full barriers
+//   warp 0        TMA producer: A half + B half per 64-wide K block into a ring of stages; both CTAs'
+//                 loads complete on the LEADER's full barrier
+//   warp 1        TMEM allocation (both CTAs); in the leader it issues the MMAs and commits to the
+//                 stage-empty barriers (multicast to both CTAs) and the accumulator-full barriers
+//   (all 32 lanes of warps 0/1 run the loops so addresses stay in uniform registers, and the issuing
+//   instructions sit under elect.sync — ptxas then emits back-to-back UTMALDG / UTCHMMA; under a lane-id
+//   test it wraps each of them in an elect/broadcast/retry loop and the MMA-issue warp, not the tensor
+//   pipe, paces the main loop: 670 instead of ≈500 cycles per K block)
 //   (epilogue warp w may only touch TMEM lanes 32·(w%4)…: quadrant = warp id % 4)
 //   warps 2..9    epilogue: TMEM → registers (one row per thread) → fused math → [32 rows × 64 B] slab in
-//                 swizzled smem → TMA store (TMA reduce-add for split-K wgrad).  Shared-memory bandwidth
-//                 is the scarce resource (the operand pipeline alone moves 64 B/clk in and 64 B/clk out
-//                 at full MMA rate), so outputs cross smem exactly twice; residual / multiplier tiles
-//                 are read two chunks ahead with coalesced loads and transposed through a third slab.
+//                 swizzled smem → TMA store (TMA reduce-add for split-K wgrad); outputs cross smem exactly
+//                 twice; residual / multiplier tiles are read two chunks ahead with coalesced loads and
+//                 transposed through a spare slab.
 //   accumulators  double-buffered in TMEM (2×BN columns) so the epilogue of tile i overlaps the MMAs
 //                 of tile i+1.
+//   schedule      static round-robin over the pairs; a 256-wide launch may mix 256- and 128-column tiles
+//                 (n_full / n_half per 256-row band, full tiles first) so that every pair gets equal work.
+//   instantiations  <BN, A_MN, B_MN, AUX>: AUX = epilogues that read a second matrix.  Separate because the
+//                 epilogue lives at the 168-register cap (10 warps → 3 per SM sub-partition).
+// Diagnostics: VITK_GEMM_DBG ablation bits (Gemm2Params::dbg) and, in builds with -DVITK_GEMM_STAMPS=1, clock
+// stamps per K block / tile / CTA / launch (tools/gemm_timeline.py).
 #include <cuda.h>
 #include <stdlib.h>
 
