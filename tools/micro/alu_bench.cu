@@ -20,6 +20,8 @@ __global__ void __launch_bounds__(1024) k(float* out, long long* cyc, int iters)
       if (MODE == 2) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a[i]));
       if (MODE == 3) asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(a[i]));
       if (MODE == 4) { a[i] = fmaf(a[i], b, c); asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(p[i].x)); }
+      if (MODE == 5) { unsigned& hx = reinterpret_cast<unsigned&>(a[i]); asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(hx)); }
+      if (MODE == 6) { unsigned& hx = reinterpret_cast<unsigned&>(a[i]); asm volatile("ex2.approx.ftz.bf16x2 %0, %0;" : "+r"(hx)); }
     }
   }
   __syncthreads();
@@ -50,5 +52,7 @@ int main() {
   run<2>("MUFU.EX2", 1);
   run<3>("MUFU.RCP", 1);
   run<4>("FFMA + MUFU.EX2 mix", 2);
+  run<5>("MUFU.EX2 f16x2", 2);
+  run<6>("MUFU.EX2 bf16x2", 2);
   return 0;
 }
