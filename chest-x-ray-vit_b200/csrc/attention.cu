@@ -96,7 +96,16 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
 
 __global__ void __launch_bounds__(kFwdThreads, 4)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_kv,
-                __nv_bfloat16* __restrict__ o, float* __restrict__ lse, int T, int H, float scale_log2) {
+                __nv_bfloat16* __restrict__ o, float* __restrict__ lse, int T, int H, float scale_log2, long long* tl) {
+  // tl (vitk_debug_timeline, ≥ 8192 int64): [3·cta + {0,1,2}] = globaltimer at entry / %smid / globaltimer at exit
+  const unsigned lin_cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+  if (tl != nullptr && threadIdx.x == 0 && lin_cta < 2000) {
+    unsigned long long t; unsigned smid;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    tl[3 * lin_cta] = static_cast<long long>(t);
+    tl[3 * lin_cta + 1] = smid;
+  }
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem + kFwdSmemQ;
@@ -322,6 +331,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
   if (warp == 4) {
     tc_fence_after_sync();
     tmem_dealloc(tmem_base, kFwdTmemCols);
+  }
+  if (tl != nullptr && threadIdx.x == 0 && lin_cta < 2000) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    tl[3 * lin_cta + 2] = static_cast<long long>(t);
   }
 }
 
@@ -720,7 +734,7 @@ extern "C" VITK_API int vitk_attn_fwd(const void* qkv, int64_t B, int64_t T, int
   }
   const dim3 grid(static_cast<unsigned>((T + kTile - 1) / kTile), static_cast<unsigned>(H), static_cast<unsigned>(B));
   VITK_CUDA(launch_pdl(attn_fwd_kernel, grid, dim3(kFwdThreads), kFwdSmemBytes, static_cast<cudaStream_t>(stream), tm, tm_kv,
-                       static_cast<__nv_bfloat16*>(o), lse, static_cast<int>(T), static_cast<int>(H), scale * kLog2e));
+                       static_cast<__nv_bfloat16*>(o), lse, static_cast<int>(T), static_cast<int>(H), scale * kLog2e, g_timeline));
   VITK_LAUNCH_CHECK("attn_fwd_kernel");
   return 0;
 }

@@ -1,6 +1,7 @@
-"""clock64 timeline of CTA (0,0,0) of the attention forward kernel (vitk_debug_timeline stamps)."""
+"""Per-CTA residency of the attention forward kernel: globaltimer at entry / exit and %smid of every CTA."""
 import os
 import sys
+from collections import defaultdict
 
 import torch
 
@@ -19,13 +20,21 @@ ops.attn_fwd(qkv, B, T, H, 0.125, o=o, lse=lse)
 torch.cuda.synchronize()
 pkg._lib.lib().vitk_debug_timeline(None)
 t = tl.cpu().tolist()
-t0 = t[2000]
-print(f"entry 0   prologue done {t[2001] - t0}   O ready {t[2002] - t0}   done {t[2003] - t0}")
-names = ["ctrl: P(u) ready", "ctrl: PV(u)+S(u+1) issued", "ctrl: K/V buffer free", "ctrl: reload issued", "w0: S(u) ready", "w0: first half done",
-         "w0: P(u) published"]
-for u in range(10):
-    print(f"--- key sub-block {u}")
-    for k, n in enumerate(names):
-        v = t[2016 + 8 * u + k]
-        if v:
-            print(f"   {n:28s} {v - t0:8d}")
+n = 5 * H * B
+rec = [(t[3 * i], t[3 * i + 1], t[3 * i + 2]) for i in range(n)]
+t0 = min(r[0] for r in rec)
+end = max(r[2] for r in rec)
+print(f"CTAs {n}; kernel span (first entry → last exit) {(end - t0) / 1e3:.1f} us")
+dur = sorted((r[2] - r[0]) / 1e3 for r in rec)
+print(f"CTA lifetime us: min {dur[0]:.1f}  median {dur[n // 2]:.1f}  p90 {dur[int(n * .9)]:.1f}  max {dur[-1]:.1f}")
+per_sm = defaultdict(list)
+for r in rec:
+    per_sm[r[1]].append(((r[0] - t0) / 1e3, (r[2] - t0) / 1e3))
+cnt = sorted(len(v) for v in per_sm.values())
+print(f"SMs {len(per_sm)}; CTAs per SM min {cnt[0]} median {cnt[len(cnt) // 2]} max {cnt[-1]}")
+last = sorted(max(e for _, e in v) for v in per_sm.values())
+print(f"per-SM finish time us: min {last[0]:.1f} median {last[len(last) // 2]:.1f} max {last[-1]:.1f}")
+starts = sorted((r[0] - t0) / 1e3 for r in rec)
+print("entry times us (every 60th CTA):", [round(x, 1) for x in starts[::60]])
+sm0 = sorted(per_sm[rec[0][1]])
+print("CTAs on the SM of CTA 0 (entry, exit us):", [(round(a, 1), round(b, 1)) for a, b in sm0])
