@@ -62,6 +62,8 @@ _PROTOS = {
     "vitk_sumsq_f32": (C.c_int, [_p, _i64, _p, _p]),
     "vitk_clip_scale": (C.c_int, [_p, _f, _p, _p]),
     "vitk_launch_count": (C.c_int64, []),
+    "vitk_gemm_plan": (C.c_int, [C.POINTER(GemmArgs), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                 C.POINTER(C.c_int)]),
     "vitk_debug_timeline": (C.c_int, [_p]),
     "vitk_debug_stamp": (C.c_int, [C.c_int64, _p]),
 }

@@ -805,3 +805,25 @@ int gemm2_try_launch(const vitk_gemm_args& a, cudaStream_t stream, bool* handled
 }
 
 }  // namespace vitk
+
+// Host-only view of the tiling decision (no device needed): which tile width, split-K factor and number of
+// half-width tiles per 256-row band vitk_gemm_bf16 would use for this problem on a GPU with `sms` SMs.
+extern "C" VITK_API int vitk_gemm_plan(const vitk_gemm_args* a, int sms, int* tile_n, int* split_k, int* n_half, int* work_items) {
+  using namespace vitk;
+  VITK_REQUIRE(a != nullptr && tile_n && split_k && n_half && work_items && sms >= 2, VITK_EINVAL, "gemm_plan: bad argument");
+  VITK_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0 && a->N % 128 == 0, VITK_EINVAL, "gemm_plan: the CTA-pair kernel needs N %% 128 == 0");
+  const int pairs = (a->max_ctas > 0 && a->max_ctas < sms ? a->max_ctas : sms) / 2;
+  int bn = 0, splits = 1, nh = 0;
+  choose_tiling2(*a, pairs, &bn, &splits, &nh);
+  VITK_REQUIRE(bn != 0, VITK_EINVAL, "gemm_plan: no CTA-pair tiling for N=%lld tile_n=%d", (long long)a->N, a->tile_n);
+  const long long m_tiles = (a->M + 2 * k2BM - 1) / (2 * k2BM);
+  const long long kb_total = (a->K + k2BK - 1) / k2BK;
+  if (splits > kb_total) splits = static_cast<int>(kb_total);
+  const long long kb_per = (kb_total + splits - 1) / splits;
+  *tile_n = bn;
+  *split_k = static_cast<int>((kb_total + kb_per - 1) / kb_per);
+  *n_half = nh;
+  *work_items = static_cast<int>(m_tiles * (a->N / bn - nh / 2 + nh) * *split_k);
+  return 0;
+}
+

@@ -111,6 +111,18 @@ def gemm(a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int, d: torch.Tens
     return d
 
 
+def gemm_plan(M: int, N: int, K: int, *, epilogue: int, b_mn_major: bool = False, a_mn_major: bool = False,
+              split_k: int = 0, tile_n: int = 0, max_ctas: int = 0, sms: int = 148) -> dict:
+    """Host-only: the tiling vitk_gemm_bf16 would pick for this problem on a GPU with ``sms`` SMs (no device needed)."""
+    g = GemmArgs()
+    g.M, g.N, g.K = M, N, K
+    g.a_mn_major, g.b_mn_major = int(a_mn_major), int(b_mn_major)
+    g.epilogue, g.split_k, g.tile_n, g.max_ctas = epilogue, split_k, tile_n, max_ctas
+    tn, sk, nh, items = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    _lib.check(_lib.lib().vitk_gemm_plan(C.byref(g), sms, C.byref(tn), C.byref(sk), C.byref(nh), C.byref(items)), "gemm_plan")
+    return {"tile_n": tn.value, "split_k": sk.value, "n_half": nh.value, "work_items": items.value}
+
+
 def colsum(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
     """out[n] += Σ_m x[m,n]  (bias gradients)."""
     M, N = x.shape
