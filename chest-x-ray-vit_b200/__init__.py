@@ -6,6 +6,10 @@ ViT-Training.py:83-132 drives.  Public surface:
   ops ................................... tensor-level wrappers over the C ABI (include/vitk.h)
   VitkAdamW ............................. flat-buffer AdamW + grad clip (optim.py)
   GradSync .............................. bucketed NCCL gradient all-reduce (parallel.py)
+  graph.GraphedTrainStep / GraphedForward  the same launch plans replayed from one CUDA graph (graph.py)
+  data.DeviceFeeder ..................... pinned-memory / copy-stream input edge (data.py)
+  checkpoint ............................ HF safetensors interchange: from_pretrained / save_pretrained (checkpoint.py)
+  metrics ............................... on-device sigmoid-threshold counters → micro-F1 (metrics.py)
   custom_ops ............................ torch.library custom ops + HF AttentionInterface plug-in
 """
 from . import _lib, ops  # noqa: F401
@@ -24,7 +28,7 @@ def __getattr__(name):
     if name == "GradSync":
         from .parallel import GradSync
         return GradSync
-    if name in ("modeling", "engine", "optim", "parallel", "custom_ops"):
+    if name in ("modeling", "engine", "optim", "parallel", "custom_ops", "graph", "data", "checkpoint", "metrics"):
         import importlib
         return importlib.import_module(f"{__name__}.{name}")
     raise AttributeError(name)

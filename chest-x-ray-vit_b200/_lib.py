@@ -56,9 +56,11 @@ _PROTOS = {
     "vitk_embed_bwd": (C.c_int, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _p]),
     "vitk_head_fwd": (C.c_int, [_p, _i64, _i64, _i64, _i64, _p, _p, _f, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "vitk_head_bwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "vitk_multilabel_counts": (C.c_int, [_p, _p, _i64, _i64, _f, _p, _p]),
     "vitk_cast_f32_bf16": (C.c_int, [_p, _p, _i64, _p]),
     "vitk_fill_zero": (C.c_int, [_p, _sz, _p]),
-    "vitk_adamw": (C.c_int, [_p, _p, _p, _p, _p, _i64, _f, _f, _f, _f, _f, _f, _f, _p, C.c_int, _p]),
+    "vitk_adamw": (C.c_int, [_p, _p, _p, _p, _p, _i64, _f, _f, _f, _f, _f, _f, _f, _p, C.c_int, _p, _p]),
+    "vitk_adamw_tick": (C.c_int, [_p, C.c_int, _f, _f, _p, _p]),
     "vitk_sumsq_f32": (C.c_int, [_p, _i64, _p, _p]),
     "vitk_clip_scale": (C.c_int, [_p, _f, _p, _p]),
     "vitk_launch_count": (C.c_int64, []),

@@ -155,3 +155,42 @@ extern "C" VITK_API int vitk_head_bwd(const float* h, const float* mean, const f
   VITK_LAUNCH_CHECK("head_bwd_kernel");
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------- evaluation counters
+// The reference's compute_metrics (ViT-Training.py:112-118) and final report (:139-146): probs = sigmoid(logits),
+// predictions = probs >= 0.5, micro-F1 / per-class precision-recall over the whole evaluation set.  Everything those
+// need is four integers per class — TP, FP, FN, TN — accumulated on the device over the batches of an evaluation loop,
+// so no logits travel to the host.  sigmoid is evaluated in fp32 as 1/(1+exp(−x)) like ATen's, so the threshold
+// comparison sees the same rounding (logits a few ulp below 0 still round to exactly 0.5 and count as positive).
+namespace vitk {
+__global__ void __launch_bounds__(256)
+multilabel_counts_kernel(const float* __restrict__ logits, const float* __restrict__ labels, long long n, int C, float threshold,
+                         unsigned long long* __restrict__ counts) {
+  extern __shared__ unsigned int s_cnt[];   // [C][4]
+  for (int i = threadIdx.x; i < 4 * C; i += blockDim.x) s_cnt[i] = 0;
+  __syncthreads();
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    const float prob = 1.0f / (1.0f + expf(-logits[i]));
+    const bool pred = prob >= threshold, truth = labels[i] >= 0.5f;
+    atomicAdd(&s_cnt[4 * c + (pred ? (truth ? 0 : 1) : (truth ? 2 : 3))], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 4 * C; i += blockDim.x)
+    if (s_cnt[i]) atomicAdd(&counts[i], static_cast<unsigned long long>(s_cnt[i]));
+}
+}  // namespace vitk
+
+extern "C" VITK_API int vitk_multilabel_counts(const float* logits, const float* labels, int64_t B, int64_t C, float threshold,
+                                               int64_t* counts, vitk_stream_t stream) {
+  VITK_REQUIRE(logits && labels && counts && B > 0 && C > 0 && C <= 4096, VITK_EINVAL, "multilabel_counts: bad argument");
+  VITK_REQUIRE(threshold > 0.f && threshold < 1.f, VITK_EINVAL, "multilabel_counts: threshold must be in (0, 1)");
+  const long long n = B * C;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 4LL * vitk::num_sms()) blocks = 4LL * vitk::num_sms();
+  vitk::multilabel_counts_kernel<<<static_cast<unsigned>(blocks), 256, 16 * C, static_cast<cudaStream_t>(stream)>>>(
+      logits, labels, n, static_cast<int>(C), threshold, reinterpret_cast<unsigned long long*>(counts));
+  VITK_LAUNCH_CHECK("multilabel_counts_kernel");
+  return 0;
+}

@@ -12,8 +12,12 @@ namespace vitk {
 __global__ void __launch_bounds__(256)
 adamw_kernel(float4* __restrict__ p, float4* __restrict__ g, float4* __restrict__ m, float4* __restrict__ v,
              uint2* __restrict__ p16, long long n4, float lr, float b1, float b2, float eps, float wd, float bc1,
-             float rsqrt_bc2, const float* __restrict__ grad_scale, int zero_grad) {
+             float rsqrt_bc2, const float* __restrict__ grad_scale, int zero_grad, const float* __restrict__ bias_corr_dev) {
   const float gs = grad_scale ? __ldg(grad_scale) : 1.0f;
+  if (bias_corr_dev) {              // CUDA-graph replay: the step counter lives on the device (adamw_tick_kernel)
+    bc1 = __ldg(bias_corr_dev);
+    rsqrt_bc2 = __ldg(bias_corr_dev + 1);
+  }
   const float step = lr / bc1, decay = 1.0f - lr * wd;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -57,6 +61,14 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float4* __restrict__ x
   }
 }
 
+// Device-side step counter for graph replay: t += inc; bc = {1 − β1^t, 1/sqrt(1 − β2^t)} (double pow, once per step).
+__global__ void adamw_tick_kernel(long long* step, int inc, float b1, float b2, float* bc) {
+  const long long t = *step + inc;
+  if (inc) *step = t;
+  bc[0] = static_cast<float>(1.0 - pow(static_cast<double>(b1), static_cast<double>(t)));
+  bc[1] = static_cast<float>(1.0 / sqrt(1.0 - pow(static_cast<double>(b2), static_cast<double>(t))));
+}
+
 // torch.nn.utils.clip_grad_norm_: coef = min(1, max_norm / (‖g‖ + 1e-6))
 __global__ void clip_scale_kernel(const float* sumsq, float max_norm, float* scale) {
   const float c = max_norm / (sqrtf(*sumsq) + 1e-6f);
@@ -69,8 +81,10 @@ using namespace vitk;
 
 extern "C" VITK_API int vitk_adamw(float* p, float* g, float* m, float* v, void* p_bf16, int64_t n, float lr,
                                    float beta1, float beta2, float eps, float weight_decay, float bias_corr1,
-                                   float bias_corr2, const float* grad_scale, int zero_grad, vitk_stream_t stream) {
+                                   float bias_corr2, const float* grad_scale, int zero_grad, const float* bias_corr_dev,
+                                   vitk_stream_t stream) {
   VITK_REQUIRE(p && g && m && v && n > 0 && n % 4 == 0, VITK_EINVAL, "adamw: n must be a positive multiple of 4");
+  if (bias_corr_dev) bias_corr1 = bias_corr2 = 1.0f;
   VITK_REQUIRE(aligned16(p) && aligned16(g) && aligned16(m) && aligned16(v) && (reinterpret_cast<uintptr_t>(p_bf16) & 7) == 0,
                VITK_EALIGN, "adamw: buffers must be 16-byte aligned");
   VITK_REQUIRE(bias_corr1 > 0.f && bias_corr2 > 0.f, VITK_EINVAL, "adamw: bias corrections must be positive");
@@ -81,8 +95,18 @@ extern "C" VITK_API int vitk_adamw(float* p, float* g, float* m, float* v, void*
   adamw_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<float4*>(p), reinterpret_cast<float4*>(g), reinterpret_cast<float4*>(m),
       reinterpret_cast<float4*>(v), static_cast<uint2*>(p_bf16), n4, lr, beta1, beta2, eps, weight_decay, bias_corr1,
-      1.0f / sqrtf(bias_corr2), grad_scale, zero_grad);
+      1.0f / sqrtf(bias_corr2), grad_scale, zero_grad, bias_corr_dev);
   VITK_LAUNCH_CHECK("adamw_kernel");
+  return 0;
+}
+
+extern "C" VITK_API int vitk_adamw_tick(int64_t* step_dev, int increment, float beta1, float beta2, float* bias_corr_dev,
+                                        vitk_stream_t stream) {
+  VITK_REQUIRE(step_dev && bias_corr_dev && beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f, VITK_EINVAL,
+               "adamw_tick: bad argument");
+  adamw_tick_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<long long*>(step_dev), increment ? 1 : 0,
+                                                                   beta1, beta2, bias_corr_dev);
+  VITK_LAUNCH_CHECK("adamw_tick_kernel");
   return 0;
 }
 

@@ -1,0 +1,96 @@
+"""Input edge of the training path: host batches → device, overlapped with compute.
+
+The reference's DataLoader hands ``collate_fn`` output — ``{"pixel_values": fp32 [B,3,H,W], "labels": fp32 [B,C]}``
+(/root/reference/ViT-Training.py:77-80) — to ``model(**batch)`` (HF trainer.py:1978).  ``DeviceFeeder`` wraps any
+iterable of such batches (or of uint8 grayscale ``[B,H,W]`` images, which is what ``img.convert("RGB")`` of a chest
+X-ray replicates three times, ViT-Training.py:60-66 — 12× fewer bytes over PCIe; the patchify kernel normalises them
+on the GPU) and yields batches already resident in HBM:
+
+  * each host batch is staged in pinned memory (a no-op when the loader already pins, ``pin_memory=True``),
+  * copied on a dedicated copy stream into one of ``depth`` device slots while the previous batch trains,
+  * and handed over with a stream-ordered event (no host synchronisation); a slot is reused only after the compute
+    stream has finished with it.
+
+Nothing here touches pixel values: normalisation / im2col happen in ``vitk_patchify_u8`` / ``vitk_patchify_f32``.
+"""
+from __future__ import annotations
+
+from typing import Dict, Iterable, Iterator, List, Optional
+
+import torch
+
+
+class DeviceFeeder:
+    def __init__(self, batches: Iterable[Dict[str, torch.Tensor]], device: Optional[torch.device] = None, depth: int = 2):
+        if depth < 2:
+            raise ValueError("DeviceFeeder: depth must be >= 2 (one slot in use, one in flight)")
+        self.batches = batches
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.depth = depth
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self._slots: List[Optional[Dict[str, torch.Tensor]]] = [None] * depth
+        self._pinned: List[Optional[Dict[str, torch.Tensor]]] = [None] * depth
+        self._ready = [torch.cuda.Event() for _ in range(depth)]
+        self._freed = [torch.cuda.Event() for _ in range(depth)]
+        self.h2d_bytes = 0              # bytes copied host → device so far
+        self.batches_fed = 0
+
+    @staticmethod
+    def _like(t: torch.Tensor, ref: Optional[torch.Tensor], **kw) -> torch.Tensor:
+        if ref is not None and ref.shape == t.shape and ref.dtype == t.dtype:
+            return ref
+        return torch.empty(t.shape, dtype=t.dtype, **kw)
+
+    def _stage(self, slot: int, batch: Dict[str, torch.Tensor]) -> None:
+        dev = self._slots[slot] or {}
+        pin = self._pinned[slot] or {}
+        new_dev, new_pin = {}, {}
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self._freed[slot])          # compute is done with this slot's previous batch
+            for k, t in batch.items():
+                if not isinstance(t, torch.Tensor):
+                    continue
+                if t.is_cuda:
+                    new_dev[k] = t
+                    continue
+                if not t.is_pinned():
+                    p = self._like(t, pin.get(k), pin_memory=True)
+                    # the slot's pinned buffer may still be the source of its previous copy: that copy was enqueued
+                    # before _freed[slot] on this stream only in program order, so wait for it on the host
+                    self._ready[slot].synchronize()
+                    p.copy_(t)
+                    new_pin[k] = p
+                    t = p
+                d = self._like(t, dev.get(k), device=self.device)
+                d.copy_(t, non_blocking=True)
+                self.h2d_bytes += t.numel() * t.element_size()
+                new_dev[k] = d
+            self._ready[slot].record(self.copy_stream)
+        self._slots[slot], self._pinned[slot] = new_dev, new_pin
+
+    def __iter__(self) -> Iterator[Dict[str, torch.Tensor]]:
+        it = iter(self.batches)
+        cur = torch.cuda.current_stream(self.device)
+        for s in range(self.depth):
+            self._freed[s].record(cur)
+        pending: List[int] = []
+        nxt = 0
+        for _ in range(self.depth - 1):                             # prime the pipeline
+            b = next(it, None)
+            if b is None:
+                break
+            self._stage(nxt, b)
+            pending.append(nxt)
+            nxt = (nxt + 1) % self.depth
+        while pending:
+            b = next(it, None)
+            if b is not None:                                       # keep one copy in flight while this batch trains
+                self._stage(nxt, b)
+                pending.append(nxt)
+                nxt = (nxt + 1) % self.depth
+            slot = pending.pop(0)
+            cur = torch.cuda.current_stream(self.device)
+            cur.wait_event(self._ready[slot])
+            self.batches_fed += 1
+            yield self._slots[slot]
+            self._freed[slot].record(torch.cuda.current_stream(self.device))

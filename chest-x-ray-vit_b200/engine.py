@@ -17,6 +17,7 @@ is also what makes the whole step capturable in a CUDA graph.
 from __future__ import annotations
 
 import ctypes as C
+import math
 from typing import Callable, Dict, List, Optional, Tuple
 
 import torch
@@ -144,8 +145,20 @@ class Arena:
             self.dpatch = new((B * P, D), bf16)
             self.dloss = new((1,), f32)
             self.dlogits_in = new((B, Cn), f32)
-            self.bwd_loss = self._build_backward(eng, from_loss=True)
-            self.bwd_logits = self._build_backward(eng, from_loss=False)
+            self._bwd_plans: Dict[Tuple[bool, bool], _Plan] = {}
+            self._eng = eng
+            self.bwd_loss = self.backward_plan(True, False)
+            self.bwd_logits = self.backward_plan(False, False)
+
+    def backward_plan(self, from_loss: bool, staged: bool) -> _Plan:
+        """Launch plan of the backward pass writing gradients into the flat buffer (staged=False) or into the
+        accumulation staging buffer (staged=True, built on first use)."""
+        key = (from_loss, staged)
+        pl = self._bwd_plans.get(key)
+        if pl is None:
+            eng = self._eng
+            pl = self._bwd_plans[key] = self._build_backward(eng, from_loss, eng.g_stage() if staged else eng.g)
+        return pl
 
     # ------------------------------------------------------------------ forward plan
     def _build_forward(self, eng: "Engine", with_labels: bool) -> _Plan:
@@ -185,8 +198,8 @@ class Arena:
         return pl
 
     # ------------------------------------------------------------------ backward plan
-    def _build_backward(self, eng: "Engine", from_loss: bool) -> _Plan:
-        cfg, w, g = eng.cfg, eng.w, eng.g
+    def _build_backward(self, eng: "Engine", from_loss: bool, g: dict) -> _Plan:
+        cfg, w = eng.cfg, eng.w
         D, Fi, H, L, Cn = cfg.hidden_size, cfg.intermediate_size, cfg.num_attention_heads, cfg.num_hidden_layers, cfg.num_labels
         T, P, B, M = cfg.seq_len, cfg.num_patches, self.B, self.M
         scale = 64 ** -0.5
@@ -291,8 +304,22 @@ class Engine:
         self.side_stream = torch.cuda.Stream(device=self.dev) if os.environ.get("VITK_SIDE_STREAM", "1") != "0" else None
         self.w = self._weight_views(model.flat_parameters(), model.shadow())
         self.g = self._weight_views(model.flat_grads(), None)
+        self._g_stage = None
         self._grad_views = {n: model.layout.view(model.flat_grads(), n) for n in model.layout.names}
         self._params = dict(model.named_parameters())
+        self._plist = model.param_list()
+        # gradient views handed to autograd: one split of the flat buffer (flat order), reshaped per parameter
+        lay = model.layout
+        by_off = sorted(lay.names, key=lambda n: lay.offset[n])
+        ends = [lay.offset[n] for n in by_off[1:]] + [lay.total]
+        self._split_sizes = [e - lay.offset[n] for n, e in zip(by_off, ends)]
+        pos = {n: i for i, n in enumerate(by_off)}
+        self._spans = [(pos[n], math.prod(lay.shapes[n]), lay.shapes[n]) for n in lay.names]     # HF order
+
+    def g_stage(self):
+        if self._g_stage is None:
+            self._g_stage = self._weight_views(self.model.stage_grads(), None)
+        return self._g_stage
 
     def _weight_views(self, flat: torch.Tensor, shadow: Optional[torch.Tensor]):
         """Kernel-facing views of a flat buffer laid out by FlatLayout.  With ``shadow`` (bf16 copy
@@ -373,51 +400,57 @@ class Engine:
         return loss, ar.logits.clone()
 
     # ------------------------------------------------------------------ backward
-    def _bind_grads(self) -> None:
-        """Make every param.grad a view of the flat gradient buffer.  A grad that is None means a
-        fresh accumulation (zero it); a foreign tensor is folded in so ``+=`` semantics hold."""
-        flat = self.model.flat_grads()
-        fresh = 0
-        foreign = []
-        for n, p in self._params.items():
-            gv = self._grad_views[n]
-            if p.grad is None:
-                fresh += 1
-            elif p.grad.data_ptr() != gv.data_ptr():
-                foreign.append((n, p.grad))
-        if fresh == len(self._params):
-            ops.fill_zero(flat)
-        elif fresh:
-            for n, p in self._params.items():
-                if p.grad is None:
-                    self._grad_views[n].zero_()
-        for n, gt in foreign:
-            self._grad_views[n].copy_(gt)
-        if fresh or foreign:
-            for n, p in self._params.items():
-                p.grad = self._grad_views[n]
+    def bind_grads(self) -> None:
+        """Fold every ``param.grad`` that lives outside the flat gradient buffer (cloned by autograd, replaced by a
+        DDP bucket view, assigned by the user) into it and re-point ``param.grad`` at the flat views, so the flat
+        optimizer sees all gradients.  Parameters whose grad is None are left alone."""
+        for p, (n, gv) in zip(self._plist, self._grad_views.items()):
+            gt = p.grad
+            if gt is not None and gt.data_ptr() != gv.data_ptr():
+                gv.copy_(gt)
+                p.grad = gv
 
-    def backward(self, ticket: int, dloss: Optional[torch.Tensor], dlogits: Optional[torch.Tensor]) -> None:
+    def backward(self, ticket: int, dloss: Optional[torch.Tensor], dlogits: Optional[torch.Tensor],
+                 needs: Optional[Tuple[bool, ...]] = None) -> tuple:
+        """Runs the backward launch plan and returns one gradient per parameter (HF order; None where ``needs`` is
+        False): fresh views of the flat buffer the kernels wrote.  If no ``param.grad`` is populated the main flat
+        buffer is used (autograd adopts the views, no copy); otherwise — gradient accumulation — the kernels write the
+        staging buffer and autograd adds it onto ``param.grad``."""
         ar = next((a for a in self.arenas.values() if a.train and a.ticket == ticket), None)
         if ar is None:
             raise RuntimeError("chest_x_ray_vit_b200: the activations of this forward were overwritten by a later "
                                "forward with the same batch size; call backward() before the next forward()")
+        n = len(self._plist)
         if dloss is None and dlogits is None:
-            return
-        self._bind_grads()
+            return (None,) * n
+        model = self.model
+        staged = any(p.grad is not None for p in self._plist)
+        if staged:
+            flat = model.stage_grads()
+            ops.fill_zero(flat)
+        else:
+            flat = model.flat_grads()
+            if not model._grads_clean:
+                ops.fill_zero(flat)
+            model._grads_clean = False
         if self.grad_sync is not None:
-            self.grad_sync.begin(self.model)
+            self.grad_sync.begin(flat)
         stream = torch.cuda.current_stream().cuda_stream
         if dloss is not None and dlogits is None:
             ar.dloss.copy_(dloss.reshape(1), non_blocking=True)
-            ar.bwd_loss.run(stream, self.side_stream)
+            ar.backward_plan(True, staged).run(stream, self.side_stream)
         else:
             if dloss is not None:      # both the loss and the logits were used downstream
                 torch.add(dlogits.to(f32), ar.dlogits * dloss.to(f32), out=ar.dlogits_in)
             else:
                 ar.dlogits_in.copy_(dlogits)
-            ar.bwd_logits.run(stream, self.side_stream)
+            ar.backward_plan(False, staged).run(stream, self.side_stream)
         ar.ticket = -1
+        if needs is None:
+            needs = (True,) * n
+        chunks = flat.split_with_sizes(self._split_sizes)
+        return tuple((chunks[i].view(sh) if chunks[i].numel() == k else chunks[i][:k].view(sh)) if nd else None
+                     for (i, k, sh), nd in zip(self._spans, needs))
 
     def _layer_grads_ready(self, l: int) -> None:
         if self.grad_sync is not None:

@@ -201,8 +201,10 @@ class ViTForImageClassification(nn.Module):
         self.num_labels = config.num_labels
         self.layout = FlatLayout(config)
         flat = torch.zeros(self.layout.total, dtype=f32)
-        self.register_buffer("_flat_params", flat, persistent=False)
+        self._flat_params = flat          # plain attribute (not a buffer: DDP would re-broadcast it every forward)
         self._flat_grads: Optional[torch.Tensor] = None
+        self._stage_grads: Optional[torch.Tensor] = None     # second gradient buffer, only for accumulation (see backward)
+        self._grads_clean = False                            # flat gradient buffer known to be all zero (VitkAdamW step)
         self._flat_shadow: Optional[torch.Tensor] = None     # bf16 copy of the 'gemm' prefix
         self._shadow_version = -1
         self._engine: Optional[Engine] = None
@@ -211,6 +213,21 @@ class ViTForImageClassification(nn.Module):
         for name in self.layout.names:
             self._register(name, nn.Parameter(self.layout.view(flat, name)))
         self.reset_parameters()
+
+    # ------------------------------------------------------------------ HF checkpoint interchange
+    @classmethod
+    def from_pretrained(cls, source, **kwargs) -> "ViTForImageClassification":
+        """``ViTForImageClassification.from_pretrained(dir_or_state_dict, num_labels=14, id2label=…, label2id=…,
+        ignore_mismatched_sizes=True, problem_type="multi_label_classification")`` as the reference calls it
+        (ViT-Training.py:83-90); see checkpoint.load_pretrained.  ``output_loading_info=True`` also returns the key report."""
+        from .checkpoint import load_pretrained
+        want_info = kwargs.pop("output_loading_info", False)
+        model, info = load_pretrained(cls, source, **kwargs)
+        return (model, info) if want_info else model
+
+    def save_pretrained(self, save_directory: str, safe_serialization: bool = True) -> None:
+        from .checkpoint import save_pretrained
+        save_pretrained(self, save_directory, safe_serialization)
 
     # ------------------------------------------------------------------ parameters
     def _register(self, name: str, p: nn.Parameter) -> None:
@@ -255,11 +272,14 @@ class ViTForImageClassification(nn.Module):
                 v.copy_(p.detach().to(f32))
                 p.data = v
                 p.grad = None
-        self._buffers["_flat_params"] = flat
+        self._flat_params = flat
         self._flat_grads = None
+        self._stage_grads = None
+        self._grads_clean = False
         self._flat_shadow = None
         self._shadow_version = -1
         self._engine = None
+        self._plist = None
 
     def flat_parameters(self) -> torch.Tensor:
         return self._flat_params
@@ -267,7 +287,20 @@ class ViTForImageClassification(nn.Module):
     def flat_grads(self) -> torch.Tensor:
         if self._flat_grads is None:
             self._flat_grads = torch.zeros_like(self._flat_params)
+            self._grads_clean = True
         return self._flat_grads
+
+    def stage_grads(self) -> torch.Tensor:
+        """Second flat gradient buffer: a backward that finds ``param.grad`` already populated (gradient
+        accumulation) writes here and autograd adds it onto ``param.grad``."""
+        if self._stage_grads is None:
+            self._stage_grads = torch.zeros_like(self._flat_params)
+        return self._stage_grads
+
+    def param_list(self) -> List[nn.Parameter]:
+        if self._plist is None:
+            self._plist = [self.get_parameter(n) for n in self.layout.names]
+        return self._plist
 
     def shadow(self) -> torch.Tensor:
         """bf16 copy of the GEMM weights, refreshed whenever the fp32 masters changed."""
@@ -282,14 +315,18 @@ class ViTForImageClassification(nn.Module):
         return self._flat_shadow
 
     def _param_version(self) -> int:
-        # in-place updates (optimizer.step, load_state_dict, init) bump each parameter's counter
-        if self._plist is None:
-            self._plist = list(self.parameters())
-        return sum(p._version for p in self._plist)
+        # in-place updates (optimizer.step, load_state_dict, init) bump each parameter's counter; writes through the
+        # flat buffer itself (broadcast_parameters, flat.copy_()) bump the buffer's
+        return sum(p._version for p in self.param_list()) + self._flat_params._version
 
     def mark_shadow_fresh(self) -> None:
         """Called by VitkAdamW, whose kernel rewrites the shadow together with the masters."""
         self._shadow_version = self._param_version()
+
+    def invalidate_shadow(self) -> None:
+        """Force the bf16 GEMM weights to be re-derived from the fp32 masters at the next forward.  Call it after
+        writing to parameter memory by a route PyTorch's version counters do not see (raw pointers, NCCL on an alias)."""
+        self._shadow_version = -1
 
     def engine(self) -> Engine:
         if self._engine is None:
@@ -335,21 +372,25 @@ class ViTForImageClassification(nn.Module):
         eng = self.engine()
         if labels is not None and self.config.problem_type is None:
             self.config.problem_type = "multi_label_classification"     # HF loss_utils.py:92-98 (float labels)
-        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.param_list())
         if need_grad:
-            loss, logits = _VitFunction.apply(self, pixel_values, labels, self.classifier.bias)
+            loss, logits = _VitFunction.apply(self, pixel_values, labels, *self.param_list())
         else:
             loss, logits = eng.forward(pixel_values, labels, save=False)
         return ImageClassifierOutput(loss=loss if labels is not None else None, logits=logits)
 
 
 class _VitFunction(torch.autograd.Function):
-    """One autograd node for the whole model: forward runs Engine.forward, backward runs
-    Engine.backward, which accumulates fp32 gradients straight into ``param.grad`` (views of one
-    flat buffer).  ``anchor`` (one parameter) is passed only so that autograd records the node."""
+    """One autograd node for the whole model.  Every parameter is an input of the node, so the usual autograd
+    contract holds: backward RETURNS one gradient per parameter that requires grad and the engine's AccumulateGrad
+    nodes populate ``param.grad`` — hooks, ``torch.autograd.grad``, frozen parameters and DistributedDataParallel's
+    reducer all see what they expect.  The returned gradients are views of one flat fp32 buffer the kernels wrote:
+    when ``param.grad`` is None autograd adopts the view without a copy, so the optimizer still finds all gradients
+    contiguous; when ``param.grad`` is already populated (gradient accumulation) the kernels write a second buffer
+    and autograd adds it in place."""
 
     @staticmethod
-    def forward(ctx, model: ViTForImageClassification, pixel_values, labels, anchor):
+    def forward(ctx, model: ViTForImageClassification, pixel_values, labels, *params):
         eng = model.engine()
         loss, logits = eng.forward(pixel_values, labels, save=True)
         ctx.model = model
@@ -363,5 +404,5 @@ class _VitFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dloss, dlogits):
         model = ctx.model
-        model.engine().backward(ctx.ticket, dloss if ctx.has_labels else None, dlogits)
-        return None, None, None, None
+        grads = model.engine().backward(ctx.ticket, dloss if ctx.has_labels else None, dlogits, ctx.needs_input_grad[3:])
+        return (None, None, None) + grads

@@ -184,6 +184,16 @@ def head_bwd(h, mean, rstd, gamma, beta, Wc, B: int, T: int, D: int, Cn: int, dl
                "head_bwd")
 
 
+def multilabel_counts(logits: torch.Tensor, labels: torch.Tensor, counts: torch.Tensor, threshold: float = 0.5):
+    """counts[c] += (TP, FP, FN, TN) of sigmoid(logits) >= threshold against {0,1} labels (ViT-Training.py:112-118)."""
+    B, Cn = logits.shape
+    assert logits.dtype == f32 and labels.dtype == f32 and labels.shape == logits.shape and logits.is_contiguous() and \
+        labels.is_contiguous() and counts.dtype == torch.int64 and counts.shape == (Cn, 4) and counts.is_contiguous()
+    _lib.check(_lib.lib().vitk_multilabel_counts(logits.data_ptr(), labels.data_ptr(), B, Cn, threshold, counts.data_ptr(),
+                                                  _stream()), "multilabel_counts")
+    return counts
+
+
 # ----------------------------------------------------------------------------- misc / optimizer
 def cast_f32_bf16(src: torch.Tensor, dst: torch.Tensor):
     _lib.check(_lib.lib().vitk_cast_f32_bf16(src.data_ptr(), dst.data_ptr(), src.numel(), _stream()), "cast_f32_bf16")
@@ -196,9 +206,16 @@ def fill_zero(t: torch.Tensor):
 
 
 def adamw(p, g, m, v, p16, n: int, lr: float, beta1: float, beta2: float, eps: float, wd: float, bc1: float, bc2: float,
-          grad_scale: Optional[torch.Tensor] = None, zero_grad: bool = False):
+          grad_scale: Optional[torch.Tensor] = None, zero_grad: bool = False, bias_corr_dev: Optional[torch.Tensor] = None):
     _lib.check(_lib.lib().vitk_adamw(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), _ptr(p16), n, lr, beta1, beta2,
-                                      eps, wd, bc1, bc2, _ptr(grad_scale), int(zero_grad), _stream()), "adamw")
+                                      eps, wd, bc1, bc2, _ptr(grad_scale), int(zero_grad), _ptr(bias_corr_dev), _stream()), "adamw")
+
+
+def adamw_tick(step_dev: torch.Tensor, increment: bool, beta1: float, beta2: float, bias_corr_dev: torch.Tensor):
+    """Device-side AdamW step counter (int64 [1]) → bias corrections (fp32 [2]) for graph replay."""
+    assert step_dev.dtype == torch.int64 and bias_corr_dev.dtype == f32 and bias_corr_dev.numel() >= 2
+    _lib.check(_lib.lib().vitk_adamw_tick(step_dev.data_ptr(), int(increment), beta1, beta2, bias_corr_dev.data_ptr(), _stream()),
+               "adamw_tick")
 
 
 def sumsq(x: torch.Tensor, out: torch.Tensor):

@@ -4,10 +4,11 @@ The reference trains 8 replicas with gradients averaged implicitly inside the XL
 step (/root/reference/ViT-Training.py:106,165,170; HF trainer.py:1760,1796).  Here every rank
 owns one GPU, the batch is sharded by rank, and the only collective of the path is an
 all-reduce (mean) of the flat fp32 gradient buffer, issued bucket by bucket while backward is
-still running: one bucket per encoder layer (its four GEMM weights are contiguous in the flat
-layout, 28.3 MB for ViT-B) in reverse layer order, then one for everything else.  NCCL runs the
-buckets on its own stream over NVLink/NVSwitch; the compute stream only waits after the last
-bucket, right before the optimizer needs the gradients.
+still running: the weight gradients of adjacent encoder layers are contiguous in the flat layout
+(28.3 MB per ViT-B layer) and are coalesced into buckets of ``layers_per_bucket`` layers (default
+3; a sequence such as (3, 3, 3, 2, 1) tapers them) in the order backward finishes them, then one
+bucket for everything else.  NCCL runs the buckets on its own stream over NVLink/NVSwitch; the
+compute stream only waits after the last bucket, right before the optimizer needs the gradients.
 """
 from __future__ import annotations
 
@@ -89,6 +90,7 @@ def broadcast_parameters(model, src: int = 0, process_group=None) -> None:
     """Identical replicas: rank ``src``'s flat fp32 parameters overwrite everyone else's."""
     if dist.is_initialized() and dist.get_world_size(process_group) > 1:
         dist.broadcast(model.flat_parameters(), src=src, group=process_group)
+        model.invalidate_shadow()       # the bf16 GEMM weights must be re-derived from the received masters
 
 
 def shard_batch(n: int, rank: int, world: int) -> Tuple[int, int]:

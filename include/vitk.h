@@ -165,16 +165,30 @@ VITK_API int vitk_head_bwd(const float* h, const float* mean, const float* rstd,
                   const float* dloss, void* dh_bf16, float* dWc, float* dbc, float* dgamma, float* dbeta,
                   vitk_stream_t stream);
 
+/* ------------------------------------------------------------------ evaluation counters
+ * Replaces compute_metrics / the final report of /root/reference/ViT-Training.py:112-118,139-146
+ * (sigmoid → >= threshold → sklearn f1_score(average="micro") / classification_report): accumulates, per class c,
+ * counts[c][0..3] += {TP, FP, FN, TN} over B×C fp32 logits and {0,1} fp32 labels.  counts: int64 [C,4], caller-zeroed
+ * before the first batch of an evaluation loop; sigmoid = 1/(1+exp(−x)) in fp32 as in ATen. */
+VITK_API int vitk_multilabel_counts(const float* logits, const float* labels, int64_t B, int64_t C, float threshold,
+               int64_t* counts, vitk_stream_t stream);
+
 /* ------------------------------------------------------------------ optimizer (flat buffers)
  * torch.optim.AdamW semantics as HF Trainer configures it (trainer.py:1143-1217,1760):
  *   g' = g·(*grad_scale)   (grad_scale: device pointer, NULL = 1; see vitk_clip_scale)
  *   p ← p·(1 − lr·wd);  m ← m + (1−β1)(g' − m);  v ← v + (1−β2)(g'² − v);
  *   p ← p − lr/bias_corr1 · m / (√v/√bias_corr2 + eps);   p_bf16 ← bf16(p) when p_bf16 != NULL;
  *   g ← 0 when zero_grad != 0 (optimizer.zero_grad() folded into the same pass).
- * n multiple of 4; all buffers 16-byte aligned. */
+ * bias_corr_dev != NULL: device pointer to {1 − β1^t, 1/√(1 − β2^t)} written by vitk_adamw_tick; the two scalar
+ * corrections are then ignored (a captured CUDA graph replays with fixed kernel arguments, so the step count must
+ * live on the device).  n multiple of 4; all buffers 16-byte aligned. */
 VITK_API int vitk_adamw(float* p, float* g, float* m, float* v, void* p_bf16, int64_t n, float lr, float beta1,
                float beta2, float eps, float weight_decay, float bias_corr1, float bias_corr2,
-               const float* grad_scale, int zero_grad, vitk_stream_t stream);
+               const float* grad_scale, int zero_grad, const float* bias_corr_dev, vitk_stream_t stream);
+/* Optimizer step counter on the device (the `step` entry of torch.optim.AdamW's state, torch/optim/adamw.py):
+ * *step_dev += increment (0 or 1); bias_corr_dev[0] = 1 − β1^t, bias_corr_dev[1] = 1/√(1 − β2^t). */
+VITK_API int vitk_adamw_tick(int64_t* step_dev, int increment, float beta1, float beta2, float* bias_corr_dev,
+               vitk_stream_t stream);
 /* out[0] += Σ x²  (global gradient norm, trainer.py:2489-2493). */
 VITK_API int vitk_sumsq_f32(const float* x, int64_t n, float* out, vitk_stream_t stream);
 /* scale[0] = min(1, max_norm / (sqrt(sumsq[0]) + 1e-6))  (torch.nn.utils.clip_grad_norm_). */

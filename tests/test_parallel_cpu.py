@@ -67,10 +67,15 @@ def _worker(rank, world, port, q):
         if rank != 0:
             with torch.no_grad():
                 m.flat_parameters().add_(1.0)
+        m._shadow_version = m._param_version()        # pretend the bf16 shadow of the pre-broadcast weights is current
         pkg.parallel.broadcast_parameters(m)
         ref = [torch.zeros_like(m.flat_parameters()) for _ in range(world)]
         dist.all_gather(ref, m.flat_parameters())
         ok_bcast = all(torch.equal(ref[0], r) for r in ref)
+        # ... and shadow() must re-derive the bf16 weights afterwards: c10d collectives do not bump tensor version
+        # counters, so the broadcast invalidates the shadow explicitly (it used to leave non-source ranks computing with
+        # their old bf16 weights)
+        ok_bcast = ok_bcast and m._shadow_version == -1
         q.put((rank, ok_mean, ok_bytes, ok_coalesced, ok_bcast))
     except Exception as e:          # surface the failure instead of a queue timeout
         q.put((rank, False, repr(e)))
