@@ -371,7 +371,7 @@ def run_ours(args):
     def timed(n, sample_clocks):
         """n steps on device-resident inputs inside one CUDA-event pair; returns (ms max over ranks, launches, clocks, loss)."""
         sampler = ClockSampler(local) if (sample_clocks and rank == 0) else None
-        n0 = pkg.ops.launch_count() + (step.kernel_launches if args.graph else 0)
+        n0 = pkg.ops.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record()
@@ -380,7 +380,7 @@ def run_ours(args):
         e1.record()
         barrier()
         t = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        launches = pkg.ops.launch_count() + (step.kernel_launches if args.graph else 0) - n0
+        launches = pkg.ops.launch_count() - n0
         clocks = sampler.stop() if sampler else None
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)

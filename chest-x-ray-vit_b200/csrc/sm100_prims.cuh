@@ -168,6 +168,21 @@ __device__ __forceinline__ void tmem_ld_wait_regs(uint32_t (&r)[16]) {
                :
                : "memory");
 }
+// Zero-instruction scheduling fence for registers filled by an earlier tcgen05.ld: placed right after tcgen05.wait::ld
+// (asm volatile statements keep their order) it makes every later use of r depend on a point past the wait, so the
+// compiler cannot hoist arithmetic on a PREFETCHED chunk above the wait that completes its load.
+__device__ __forceinline__ void tmem_regs_ready(uint32_t (&r)[32]) {
+  asm volatile(""
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+  asm volatile(""
+               : "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                 "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&r)[8]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"

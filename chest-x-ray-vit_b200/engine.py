@@ -18,6 +18,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Callable, Dict, List, Optional, Tuple
 
 import torch
@@ -27,6 +28,7 @@ from ._lib import (EPI_ACCUM_F32, EPI_BIAS_BF16, EPI_BIAS_GELUG_BF16, EPI_BIAS_R
                    EPI_STORE_BF16, GemmArgs)
 
 bf16, f32 = torch.bfloat16, torch.float32
+_PLAN_GRAPHS = os.environ.get("VITK_PLAN_GRAPHS", "1") != "0"
 
 
 class _Plan:
@@ -36,6 +38,8 @@ class _Plan:
         self.steps: List[Tuple[object, tuple, str]] = []
         self.gemm_flops: Dict[int, float] = {}      # step index → 2·M·N·K (bench.py's roofline leg)
         self.side_steps = set()                     # indices of steps launched on the side stream
+        self._segments = {}                         # (callbacks?, side stream?) → [(CUDAGraph | None, callback | None)]
+        self._warm = set()
         self._keep = []      # keeps GemmArgs structs alive
         self._side = False
 
@@ -76,12 +80,14 @@ class _Plan:
     def call(self, fn: Callable[[], None]):
         self.steps.append((None, (fn,), "python"))
 
-    def run(self, stream: int, side_stream: Optional[torch.cuda.Stream] = None):
+    def _run_range(self, lo: int, hi: int, stream: int, side_stream: Optional[torch.cuda.Stream], run_py: bool = True):
         side = side_stream.cuda_stream if side_stream is not None else stream
-        for i, (fn, args, name) in enumerate(self.steps):
+        for i in range(lo, hi):
+            fn, args, name = self.steps[i]
             if fn is None:
                 if name == "python":
-                    args[0]()
+                    if run_py:
+                        args[0]()
                 elif side_stream is not None:
                     main = torch.cuda.current_stream()
                     ev = torch.cuda.Event()
@@ -95,6 +101,53 @@ class _Plan:
             rc = fn(*args, side if i in self.side_steps else stream)
             if rc != 0:
                 _lib.check(rc, name)
+
+    def run(self, stream: int, side_stream: Optional[torch.cuda.Stream] = None, callbacks: bool = True):
+        """Enqueue the plan on the current stream.  The first call launches kernel by kernel (it also initialises
+        per-kernel attributes and the tensor-map cache); the second call captures every run of launches between two
+        Python callbacks into a CUDA graph (side-stream forks/joins become parallel branches), and from then on a
+        plan costs one cudaGraphLaunch per segment instead of one ctypes call + cudaLaunchKernelEx per kernel
+        (≈140 per plan).  ``callbacks=False`` skips the Python callbacks (no gradient sync attached): one segment.
+        VITK_PLAN_GRAPHS=0 keeps the kernel-by-kernel path."""
+        if not _PLAN_GRAPHS or torch.cuda.is_current_stream_capturing():
+            self._run_range(0, len(self.steps), stream, side_stream, callbacks)
+            return
+        key = (callbacks, side_stream is not None)
+        segs = self._segments.get(key)
+        if segs is None:
+            if key not in self._warm:
+                self._warm.add(key)
+                self._run_range(0, len(self.steps), stream, side_stream, callbacks)
+                return
+            segs = self._segments[key] = self._capture(side_stream, callbacks)
+        for g, fn in segs:
+            if fn is None:
+                g[0].replay()
+                ops.note_graph_replay(g[1])
+            else:
+                fn()
+
+    def _capture(self, side_stream, callbacks: bool):
+        bounds, lo = [], 0
+        for i, (fn, args, name) in enumerate(self.steps):
+            if fn is None and name == "python" and callbacks:
+                if i > lo:
+                    bounds.append((lo, i, None))
+                bounds.append((i, i + 1, args[0]))
+                lo = i + 1
+        if lo < len(self.steps):
+            bounds.append((lo, len(self.steps), None))
+        segs = []
+        for lo, hi, cb in bounds:
+            if cb is not None:
+                segs.append((None, cb))
+                continue
+            g = torch.cuda.CUDAGraph()
+            n0 = ops.direct_launch_count()
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                self._run_range(lo, hi, torch.cuda.current_stream().cuda_stream, side_stream, run_py=False)
+            segs.append(((g, ops.direct_launch_count() - n0), None))
+        return segs
 
 
 def _p(t: Optional[torch.Tensor]):
@@ -300,7 +353,6 @@ class Engine:
         self.ticket = 0
         self.arenas: Dict[Tuple[int, bool], Arena] = {}
         self.grad_sync = None            # parallel.GradSync, set by the caller for N>1
-        import os
         self.side_stream = torch.cuda.Stream(device=self.dev) if os.environ.get("VITK_SIDE_STREAM", "1") != "0" else None
         self.w = self._weight_views(model.flat_parameters(), model.shadow())
         self.g = self._weight_views(model.flat_grads(), None)
@@ -364,7 +416,6 @@ class Engine:
         0 = no cap (single GPU)."""
         if self.grad_sync is None or getattr(self.grad_sync, "world", 1) == 1:
             return 0
-        import os
         reserve = int(os.environ.get("VITK_COMM_SMS", "0"))   # measured at N=4: reserving 8–32 SMs costs more than it saves
         sms = torch.cuda.get_device_properties(self.dev).multi_processor_count
         return max(2, sms - reserve) if reserve > 0 else 0
@@ -438,13 +489,13 @@ class Engine:
         stream = torch.cuda.current_stream().cuda_stream
         if dloss is not None and dlogits is None:
             ar.dloss.copy_(dloss.reshape(1), non_blocking=True)
-            ar.backward_plan(True, staged).run(stream, self.side_stream)
+            ar.backward_plan(True, staged).run(stream, self.side_stream, callbacks=self.grad_sync is not None)
         else:
             if dloss is not None:      # both the loss and the logits were used downstream
                 torch.add(dlogits.to(f32), ar.dlogits * dloss.to(f32), out=ar.dlogits_in)
             else:
                 ar.dlogits_in.copy_(dlogits)
-            ar.backward_plan(False, staged).run(stream, self.side_stream)
+            ar.backward_plan(False, staged).run(stream, self.side_stream, callbacks=self.grad_sync is not None)
         ar.ticket = -1
         if needs is None:
             needs = (True,) * n

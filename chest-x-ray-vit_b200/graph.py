@@ -56,11 +56,11 @@ class GraphedForward:
             _patchify_into(model, self.ar, example.to(eng.dev))
             self.ar.fwd.run(stream.cuda_stream)
         torch.cuda.current_stream().wait_stream(stream)
-        n0 = ops.launch_count()
+        n0 = ops.direct_launch_count()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.ar.fwd.run(torch.cuda.current_stream().cuda_stream)
-        self.launches_per_replay = ops.launch_count() - n0
+        self.launches_per_replay = ops.direct_launch_count() - n0
         self.replays = 0
 
     def __call__(self, pixel_values: torch.Tensor) -> torch.Tensor:
@@ -73,6 +73,7 @@ class GraphedForward:
             pixel_values = pixel_values.to(self.ar.apatch.device, non_blocking=True)
         _patchify_into(model, self.ar, pixel_values)
         self.graph.replay()
+        ops.note_graph_replay(self.launches_per_replay)
         self.replays += 1
         return self.ar.logits.clone()
 
@@ -119,14 +120,14 @@ class GraphedTrainStep:
             ops.fill_zero(g)
         torch.cuda.current_stream().wait_stream(stream)
         torch.cuda.synchronize()
-        n0 = ops.launch_count()
+        n0 = ops.direct_launch_count()
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             s = torch.cuda.current_stream().cuda_stream
             ar.fwd_loss.run(s)
             ar.backward_plan(True, False).run(s, eng.side_stream)
             opt._enqueue(g, p, segs, True, 0, (self._step_dev, self._bc_dev))
-        n = ops.launch_count() - n0
+        n = ops.direct_launch_count() - n0
         model._grads_clean = True
         return graph, ar, n
 
@@ -151,6 +152,7 @@ class GraphedTrainStep:
         opt._step += 1
         model.mark_shadow_fresh()
         model._grads_clean = True
+        ops.note_graph_replay(n)
         self.replays += 1
         self.kernel_launches += n
         return ar.loss[0]

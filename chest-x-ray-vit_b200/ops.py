@@ -27,8 +27,22 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
+_replayed_launches = 0
+
+
 def launch_count() -> int:
+    """Kernels of libvitk launched so far by this process: the library's own counter (one per kernel launch call)
+    plus the kernel nodes executed by CUDA-graph replays (counted when the graph was captured)."""
+    return int(_lib.lib().vitk_launch_count()) + _replayed_launches
+
+
+def direct_launch_count() -> int:
     return int(_lib.lib().vitk_launch_count())
+
+
+def note_graph_replay(kernel_nodes: int) -> None:
+    global _replayed_launches
+    _replayed_launches += kernel_nodes
 
 
 def check_device(dev: int = 0) -> None:

@@ -155,8 +155,10 @@ def _train_steps(m, opt, x, y, n, clip=None, loss_scale=1.0):
 @pytest.mark.parametrize("clip,loss_scale", [(None, 1.0), (1.0, 1.0), (1.0, 1e-3)])
 def test_vitk_adamw_matches_torch_adamw_with_clip(clip, loss_scale):
     """VitkAdamW(max_grad_norm) — the optimizer bench.py times — against clip_grad_norm_ + torch.optim.AdamW
-    (HF trainer.py:1755-1760) on two identical replicas: post-step parameters after 3 steps.  With loss_scale 1 the
-    global gradient norm is 2.24 (> 1: the clip is active); with 1e-3 it is inactive."""
+    (HF trainer.py:1755-1760) on IDENTICAL gradients, three steps: replica A computes the gradients, replica B receives
+    copies of them as ordinary ``param.grad`` tensors (which also exercises the fold of foreign gradients into the flat
+    buffer).  Same gradients in, so the post-step parameters must agree to fp32 rounding.  With loss_scale 1 the global
+    gradient norm is 2.24 (> 1: the clip is active); with 1e-3 it is inactive and eps matters."""
     rec = torch.load(os.path.join(GOLD, "tiny_b3.pt"), weights_only=False)
     cfg = O.OracleConfig(**rec["cfg"])
     import chest_x_ray_vit_b200 as pkg
@@ -169,27 +171,61 @@ def test_vitk_adamw_matches_torch_adamw_with_clip(clip, loss_scale):
     dc = [p for n, p in ma.named_parameters() if ma.layout.kinds[n] != "nodecay"]
     oa = torch.optim.AdamW([{"params": dc, "weight_decay": 0.01}, {"params": nd, "weight_decay": 0.0}], lr=lr,
                            betas=(0.9, 0.999), eps=1e-8)
-    la = _train_steps(ma, oa, x, y, 1, clip=clip, loss_scale=loss_scale)
-    lb = _train_steps(mb, ob, x, y, 1, clip=None, loss_scale=loss_scale)
-    if clip is not None:
-        gn = ob.grad_norm().item()
-        assert (gn > 1.0) == (loss_scale == 1.0), gn                  # the case really exercises clip on / clip off
-    la += _train_steps(ma, oa, x, y, 2, clip=clip, loss_scale=loss_scale)
-    lb += _train_steps(mb, ob, x, y, 2, clip=None, loss_scale=loss_scale)
-    assert la[2] < la[0] and abs(la[2] - lb[2]) < 1e-4
-    worst = 0.0
-    for (k, pa), (_, pb) in zip(ma.named_parameters(), mb.named_parameters()):
-        d = (pa.detach() - pb.detach()).abs().max().item()
-        worst = max(worst, d)
-        assert d <= 0.05 * lr, (k, d)               # 3 steps move a parameter by up to 3·lr; replicas agree to 5 % of one step
-    print(f"VitkAdamW vs torch AdamW (clip={clip}, loss_scale={loss_scale}): max |Δparam| after 3 steps {worst:.3e}")
+    worst, losses = 0.0, []
+    for it in range(3):
+        out = ma(pixel_values=x, labels=y)
+        (out.loss * loss_scale).backward()
+        losses.append(out.loss.item())
+        for pa, pb in zip(ma.parameters(), mb.parameters()):
+            pb.grad = pa.grad.detach().clone()
+        if clip is not None:
+            total = torch.nn.utils.clip_grad_norm_(ma.parameters(), clip).item()
+        oa.step()
+        ob.step()
+        if clip is not None:
+            gn = ob.grad_norm().item()
+            assert abs(gn / total - 1) < 1e-4, (gn, total)
+            if it == 0:
+                assert (gn > 1.0) == (loss_scale == 1.0), gn          # the case really exercises clip on / clip off
+        oa.zero_grad(set_to_none=True)
+        ob.zero_grad(set_to_none=True)
+        for (k, pa), (_, pb) in zip(ma.named_parameters(), mb.named_parameters()):
+            d = (pa.detach() - pb.detach()).abs().max().item()
+            worst = max(worst, d)
+            assert d <= 2e-3 * lr, (it, k, d)           # a step moves a parameter by up to lr; 0.2 % of that
+    assert losses[2] < losses[0]
+    print(f"VitkAdamW vs torch AdamW (clip={clip}, loss_scale={loss_scale}): max |Δparam| over 3 steps {worst:.3e}")
+
+
+def test_vitk_adamw_trajectory_tracks_torch_adamw():
+    """Two independently trained replicas (eager torch AdamW + clip_grad_norm_ vs VitkAdamW(max_grad_norm=1)), three
+    steps each on their OWN gradients.  Gradients are reproducible only up to the order of fp32 atomics (bf16
+    roundings downstream flip), and Adam turns a sign-uncertain gradient element into a ±lr difference, so the
+    comparison is statistical: losses agree, and all but a small fraction of elements agree to a tenth of a step."""
+    rec = torch.load(os.path.join(GOLD, "tiny_b3.pt"), weights_only=False)
+    cfg = O.OracleConfig(**rec["cfg"])
+    import chest_x_ray_vit_b200 as pkg
+    x, y = rec["x8"][:, 0].cuda(), rec["y"].cuda()
+    lr = 1e-3
+    ma, mb = _model(cfg, O.init_params(cfg, 0, 123)), _model(cfg, O.init_params(cfg, 0, 123))
+    oa = torch.optim.AdamW(ma.parameters(), lr=lr, weight_decay=0.0)
+    ob = pkg.VitkAdamW(mb, lr=lr, weight_decay=0.0, max_grad_norm=1.0)
+    la = _train_steps(ma, oa, x, y, 3, clip=1.0)
+    lb = _train_steps(mb, ob, x, y, 3)
+    assert la[0] == lb[0] and la[2] < la[0] and abs(la[2] - lb[2]) < 1e-4, (la, lb)
+    da = torch.cat([(pa.detach() - pb.detach()).abs().flatten() for pa, pb in zip(ma.parameters(), mb.parameters())])
+    frac = (da > 0.1 * lr).float().mean().item()
+    print(f"trajectories after 3 steps: {100 * frac:.3f}% of elements differ by more than lr/10, mean |Δ| {da.mean().item():.2e}")
+    assert frac < 0.02 and da.mean().item() < 0.02 * lr and da.max().item() <= 6.5 * lr
 
 
 def test_vitk_adamw_clip_post_step_matches_hf_goldens():
     """One VitkAdamW(max_grad_norm=1.0) step against the post-step parameters frozen from HF + torch.optim.AdamW on the
     CPU: the tiny config (every element) and ViT-B/16@384 batch 2 (64 sampled elements per parameter).  The goldens were
     stepped without clipping; a first AdamW step moves every element by lr·g/(|g|+eps), which a positive rescale of g
-    leaves unchanged except where |g| ~ eps, hence the same atol with the clip active (global norms 2.24 and 11.4)."""
+    leaves unchanged except where |g| ~ eps, hence the same tolerance with the clip active (global norms 2.24 and 11.4).
+    An element is "off" when it differs by more than half a step, i.e. its gradient had the other sign than HF's fp32
+    one (bf16 noise on a near-zero gradient): at most 2 % of all elements, 10 % of any one parameter."""
     import chest_x_ray_vit_b200 as pkg
     from oracle.make_golden import sample_indices
     for fname in ("tiny_b3.pt", "vitb16_384_b2.pt"):
@@ -211,9 +247,10 @@ def test_vitk_adamw_clip_post_step_matches_hf_goldens():
                 v = rec["post_sample"][k]
                 p = p.flatten()[sample_indices(k, p.numel())]
             nb = ((p - v).abs() > 1.0e-5).sum().item()
-            assert nb <= 0.02 * v.numel() + 1, (fname, k, nb, v.numel())
+            assert nb <= 0.10 * v.numel() + 1, (fname, k, nb, v.numel())
             bad, tot = bad + nb, tot + v.numel()
         print(f"{fname}: {bad}/{tot} post-step elements off by more than lr/2")
+        assert bad <= 0.02 * tot, (fname, bad, tot)
 
 
 def test_vitk_adamw_state_dict_round_trip():
@@ -239,12 +276,14 @@ def test_vitk_adamw_state_dict_round_trip():
     ob.load_state_dict(sd_o)
     _train_steps(ma, oa, x, y, 1)
     _train_steps(mb, ob, x, y, 1)
-    for (k, pa), (_, pb) in zip(ma.named_parameters(), mb.named_parameters()):
-        assert (pa - pb).abs().max().item() <= 2e-6, k
+    def mean_diff(a, b):
+        return torch.cat([(pa.detach() - pb.detach()).abs().flatten() for pa, pb in zip(a.parameters(), b.parameters())]).mean().item()
+    # the two replicas recompute their own (atomics-order-dependent) gradients, so compare on average, not element by element
+    assert mean_diff(ma, mb) < 2e-5, mean_diff(ma, mb)
     mc = _model(cfg, sd_m)                          # without the state the trajectories differ (guards against a vacuous pass)
     oc = pkg.VitkAdamW(mc, lr=1e-3, max_grad_norm=1.0)
     _train_steps(mc, oc, x, y, 1)
-    assert max((pa - pc).abs().max().item() for pa, pc in zip(ma.parameters(), mc.parameters())) > 1e-4
+    assert mean_diff(ma, mc) > 1e-4, mean_diff(ma, mc)
 
 
 def test_autograd_contract_hooks_frozen_params_and_autograd_grad():

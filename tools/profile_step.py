@@ -5,6 +5,8 @@ import sys
 
 import torch
 
+os.environ.setdefault("VITK_PLAN_GRAPHS", "0")   # kernel-by-kernel launches: ncu sees the step in launch order
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import chest_x_ray_vit_b200 as pkg  # noqa: E402
 
