@@ -73,10 +73,14 @@ __device__ __forceinline__ void store_row32_sw128(uint8_t* tile, int row, int co
 //   warps 0-3 / 4-7 : softmax warpgroup of tile 0 / tile 1 (thread = query row = TMEM lane)
 //   warp 8          : MMA issue        warp 9 : TMA loads (Q tiles once, then a 3-deep ring of K and of V blocks)
 //   S_t  = Q_t·Kᵀ     SS-MMA, N = 128 keys (65 cycles per 16-wide k-step instead of 2 × 49 for two N = 64 MMAs)
-//   P_t  (bf16)       written back INTO the consumed S_t columns with tcgen05.st (two per 32-bit column)
+//   P_t  (bf16)       written to its own TMEM columns with tcgen05.st (two per 32-bit column).  P does not alias S:
+//                     the warpgroup releases S_t as soon as its last chunk sits in registers (≈ one chunk of math
+//                     before P_t is complete), so S_t of the NEXT block is computed while this block's softmax finishes
+//                     and the warpgroup never waits for the tensor core in steady state
 //   O_t += P_t·V      TS-MMA: A = P straight from TMEM, B = V rows from smem (MN-major); O_t stays in TMEM for the
 //                     whole key loop — no read-back per block, no P round trip through shared memory
-// TMEM columns: S0/P0 [0,128)  S1/P1 [128,256)  O0 [256,320)  O1 [320,384).
+// TMEM columns (all 512): S0 [0,128)  S1 [128,256)  P0 [256,320)  P1 [320,384)  O0 [384,448)  O1 [448,512).
+// Epilogue: O_t/l → bf16 → the (now idle) Q_t tile in shared memory → one TMA store per tile (rows ≥ T clipped).
 // Softmax is single-pass with a lazily updated reference maximum: probabilities are taken relative to m_ref; whenever
 // a 32-column chunk exceeds it by more than 2^16 (always on the very first chunk, otherwise only for extreme logits)
 // everything accumulated so far is rescaled by 2^(old−new) ≤ 1 — exact bookkeeping, m_ref cancels in O/l and in the
@@ -139,7 +143,8 @@ __device__ __forceinline__ void softmax_pairs(const uint32_t (&r)[32], float sca
 
 __global__ void __launch_bounds__(kFwdThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_kv,
-                __nv_bfloat16* __restrict__ o, float* __restrict__ lse, int T, int H, int BH, float scale_log2, long long* tl) {
+                const __grid_constant__ CUtensorMap tma_o, float* __restrict__ lse, int T, int H, int BH, float scale_log2,
+                long long* tl) {
   // tl (vitk_debug_timeline, ≥ 8192 int64): [3·cta + {0,1,2}] = globaltimer at entry / %smid / globaltimer at exit
   const unsigned lin_cta = blockIdx.x;
   if (tl != nullptr && threadIdx.x == 0 && lin_cta < 2000) {
@@ -163,7 +168,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
   uint64_t* bar_p = bar_s + 2;                // [2] P_t written by the 4 warps of warpgroup t
   uint64_t* bar_pv = bar_p + 2;               // [2] P·V_t of a block retired (only the rescale path waits on it)
   uint64_t* bar_o = bar_pv + 2;               // [2] last P·V_t retired
-  constexpr int kNumBars = 2 + 4 * kStages + 8;
+  uint64_t* bar_sfree = bar_o + 2;            // [2] S_t of the current block fully read into registers by warpgroup t
+  constexpr int kNumBars = 2 + 4 * kStages + 10;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_q + kNumBars);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -182,7 +188,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
   if (tid == 0) {
     tma_prefetch_desc(&tma_q);
     tma_prefetch_desc(&tma_kv);
-    for (int i = 0; i < kNumBars; ++i) mbar_init(bar_q + i, (bar_q + i >= bar_p && bar_q + i < bar_pv) ? 4 : 1);
+    tma_prefetch_desc(&tma_o);
+    for (int i = 0; i < kNumBars; ++i)
+      mbar_init(bar_q + i, ((bar_q + i >= bar_p && bar_q + i < bar_pv) || bar_q + i >= bar_sfree) ? 4 : 1);
     fence_mbar_init();
   }
   if (warp == 8) tmem_alloc(tmem_slot, kFwdTmemCols);
@@ -252,11 +260,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
       mbar_wait(&bar_v[st], ph);
       if (j + 1 < nblk) mbar_wait(&bar_k[(j + 1) % kStages], ((j + 1) / kStages) & 1);
       for (int t = 0; t < ntl; ++t) {
-        VITK_FSTAMP(16 * j + 8 + 3 * t + 0);                      // MMA warp: waiting for P_t(j)
+        if (j + 1 < nblk) {                     // S_t(j+1) as soon as warpgroup t holds all of S_t(j) in registers
+          VITK_FSTAMP(16 * j + 8 + 3 * t + 0);
+          mbar_wait(&bar_sfree[t], j & 1);
+          tc_fence_after_sync();
+          issue_s(t, j + 1);
+        }
         mbar_wait(&bar_p[t], j & 1);
         tc_fence_after_sync();
         VITK_FSTAMP(16 * j + 8 + 3 * t + 1);                      // got P_t(j)
-        const uint32_t tm_p = tmem_base + t * 128, tm_o = tmem_base + 256 + t * kDh;
+        const uint32_t tm_p = tmem_base + 256 + t * 64, tm_o = tmem_base + 384 + t * kDh;
         if (elect_one()) {
           if (ksteps == kKB / 16) {             // full block: unrolled, MMAs issue back to back
 #pragma unroll
@@ -270,8 +283,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
           if (t == ntl - 1) tc_commit(&bar_vfree[st]);
           if (j == nblk - 1) tc_commit(&bar_o[t]);
         }
-        if (j + 1 < nblk) issue_s(t, j + 1);    // queued right behind P·V_t(j), which reads the P aliased into S_t
-        VITK_FSTAMP(16 * j + 8 + 3 * t + 2);                      // P·V_t(j), S_t(j+1) issued
+        VITK_FSTAMP(16 * j + 8 + 3 * t + 2);                      // S_t(j+1), P·V_t(j) issued
       }
     }
     __syncwarp();
@@ -282,7 +294,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
       const int row = tid - t * kFwdWG;       // query row inside the tile = TMEM lane
       const uint32_t lane_field = static_cast<uint32_t>((warp & 3) * 32) << 16;
       const uint32_t tm_s = tmem_base + lane_field + t * 128;
-      const uint32_t tm_o = tmem_base + lane_field + 256 + t * kDh;
+      const uint32_t tm_p = tmem_base + lane_field + 256 + t * 64;
+      const uint32_t tm_o = tmem_base + lane_field + 384 + t * kDh;
+      bool p_free = true;                     // P·V_t of the previous block has finished reading the P columns
       float m_ref = -INFINITY, l_run = 0.f;
       for (int j = 0; j < nblk; ++j) {
         const int nvalid = min(kKB, T - j * kKB);
@@ -324,8 +338,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
             tmem_st_wait();                         // P chunks of this block written so far
             if (j > 0) {
               // O_t holds P·V of blocks < j; P·V_t(j-1) may still be in flight
-              mbar_wait(&bar_pv[t], (j - 1) & 1);
-              tc_fence_after_sync();
+              if (!p_free) {
+                mbar_wait(&bar_pv[t], (j - 1) & 1);
+                tc_fence_after_sync();
+                p_free = true;
+              }
 #pragma unroll 1
               for (int cc = 0; cc < 2; ++cc) {
                 uint32_t ro[32];
@@ -339,14 +356,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
 #pragma unroll 1
             for (int cc = 0; cc < c; ++cc) {        // P chunks of this block already written
               uint32_t pq[16];
-              tmem_ld_32x16(tm_s + cc * 16, pq);
+              tmem_ld_32x16(tm_p + cc * 16, pq);
               tmem_ld_wait();
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
                 const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pq[i]));
                 pq[i] = pack_bf16x2(f.x * alpha, f.y * alpha);
               }
-              tmem_st_32x16(tm_s + cc * 16, pq);
+              tmem_st_32x16(tm_p + cc * 16, pq);
             }
             m_ref = m_new;
           }
@@ -365,7 +382,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
           }
           rs0 += s0;
           rs1 += s1;
-          tmem_st_32x16(tm_s + c * 16, pk);     // chunk c of P → columns [16c, 16c+16): S columns already consumed
+          if (!p_free) {                        // first P chunk of this block: P·V_t(j-1) must be done with the P columns
+            mbar_wait(&bar_pv[t], (j - 1) & 1);
+            tc_fence_after_sync();
+            p_free = true;
+          }
+          tmem_st_32x16(tm_p + c * 16, pk);     // chunk c of P → P columns [16c, 16c+16)
+        };
+        auto release_s = [&]() {                // every lane of this warp has its part of S_t(j) in registers
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar_sfree[t]);
         };
         // two register buffers: the next chunk's TMEM load is in flight during this chunk's math
         uint32_t ra[32], rb[32];
@@ -373,15 +400,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
         for (int c = 0; c < nchunk; c += 2) {
           tmem_ld_wait();
           tmem_regs_ready(ra);
-          if (c + 1 < nchunk) tmem_ld_32x32(tm_s + (c + 1) * 32, rb);
+          if (c + 1 < nchunk) tmem_ld_32x32(tm_s + (c + 1) * 32, rb); else release_s();
           chunk(ra, c);
           if (c + 1 < nchunk) {
             tmem_ld_wait();
             tmem_regs_ready(rb);
-            if (c + 2 < nchunk) tmem_ld_32x32(tm_s + (c + 2) * 32, ra);
+            if (c + 2 < nchunk) tmem_ld_32x32(tm_s + (c + 2) * 32, ra); else release_s();
             chunk(rb, c + 1);
           }
         }
+        p_free = false;
         l_run += rs0 + rs1;
         if ((warp & 3) == 0) VITK_FSTAMP(16 * j + 4 * t + 2);      // math done
         tmem_st_wait();
@@ -395,23 +423,29 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
       if ((warp & 3) == 0) VITK_FSTAMP(201 + 2 * t);                  // last P·V_t retired
       const int tq = (tile0 + t) * kTile + row;
       const float inv = 1.0f / l_run;
+      // O_t / l → bf16 → Q_t's shared-memory tile (every S_t MMA that read it has retired), 128-byte swizzled rows
+      uint8_t* srow = sQ + t * kTileBytes + row * 128;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         uint32_t ro[32];
         tmem_ld_32x32(tm_o + c * 32, ro);
         tmem_ld_wait();
-        if (tq < T) {
-          uint4* dst = reinterpret_cast<uint4*>(o + ((static_cast<long long>(b) * T + tq) * H + h) * kDh + c * 32);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint4 w;
-            w.x = pack_bf16x2(__uint_as_float(ro[8 * q + 0]) * inv, __uint_as_float(ro[8 * q + 1]) * inv);
-            w.y = pack_bf16x2(__uint_as_float(ro[8 * q + 2]) * inv, __uint_as_float(ro[8 * q + 3]) * inv);
-            w.z = pack_bf16x2(__uint_as_float(ro[8 * q + 4]) * inv, __uint_as_float(ro[8 * q + 5]) * inv);
-            w.w = pack_bf16x2(__uint_as_float(ro[8 * q + 6]) * inv, __uint_as_float(ro[8 * q + 7]) * inv);
-            dst[q] = w;
-          }
+        for (int q = 0; q < 4; ++q) {
+          uint4 w;
+          w.x = pack_bf16x2(__uint_as_float(ro[8 * q + 0]) * inv, __uint_as_float(ro[8 * q + 1]) * inv);
+          w.y = pack_bf16x2(__uint_as_float(ro[8 * q + 2]) * inv, __uint_as_float(ro[8 * q + 3]) * inv);
+          w.z = pack_bf16x2(__uint_as_float(ro[8 * q + 4]) * inv, __uint_as_float(ro[8 * q + 5]) * inv);
+          w.w = pack_bf16x2(__uint_as_float(ro[8 * q + 6]) * inv, __uint_as_float(ro[8 * q + 7]) * inv);
+          *reinterpret_cast<uint4*>(srow + (((4 * c + q) ^ (row & 7)) << 4)) = w;
         }
+      }
+      fence_proxy_async_smem();
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + t), "r"(kFwdWG) : "memory");
+      if (row == 0) {
+        tma_store_3d(&tma_o, sQ + t * kTileBytes, colq, (tile0 + t) * kTile, b);
+        tma_store_commit();
+        tma_store_wait_read<0>();
       }
       if (tq < T) lse[(static_cast<long long>(b) * H + h) * T + tq] = (m_ref + log2f(l_run)) * kLn2;
       if ((warp & 3) == 0) VITK_FSTAMP(202 + 2 * t);                  // O_t stored
@@ -815,8 +849,9 @@ extern "C" VITK_API int vitk_attn_fwd(const void* qkv, int64_t B, int64_t T, int
   if (int rc = check_shape("attn_fwd", B, T, H)) return rc;
   VITK_REQUIRE(aligned16(qkv) && aligned16(o), VITK_EALIGN, "attn_fwd: buffers must be 16-byte aligned");
   VITK_REQUIRE(scale > 0.f, VITK_EINVAL, "attn_fwd: scale must be positive");
-  CUtensorMap tm;      // one box shape serves Q tiles and K/V blocks: 128 rows × 64 columns
+  CUtensorMap tm, tm_o;      // one box shape (128 rows × 64 columns) serves Q tiles, K/V blocks and the O store
   if (int rc = qkv_tensor_map(&tm, qkv, B, T, 3 * H * kDh)) return rc;
+  if (int rc = qkv_tensor_map(&tm_o, o, B, T, H * kDh)) return rc;
   static std::atomic<int> attr_done{0};
   if (!attr_done.load()) {
     VITK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmemBytes));
@@ -826,7 +861,7 @@ extern "C" VITK_API int vitk_attn_fwd(const void* qkv, int64_t B, int64_t T, int
   const int64_t units = B * H * ((ntile >> 1) + (ntile & 1));
   VITK_REQUIRE(units < (1LL << 31), VITK_EINVAL, "attn_fwd: too many work units");
   VITK_CUDA(launch_pdl(attn_fwd_kernel, dim3(static_cast<unsigned>(units)), dim3(kFwdThreads), kFwdSmemBytes,
-                       static_cast<cudaStream_t>(stream), tm, tm, static_cast<__nv_bfloat16*>(o), lse, static_cast<int>(T),
+                       static_cast<cudaStream_t>(stream), tm, tm, tm_o, lse, static_cast<int>(T),
                        static_cast<int>(H), static_cast<int>(B * H), scale * kLog2e, g_timeline));
   VITK_LAUNCH_CHECK("attn_fwd_kernel");
   return 0;

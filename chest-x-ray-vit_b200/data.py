@@ -45,6 +45,12 @@ class DeviceFeeder:
         dev = self._slots[slot] or {}
         pin = self._pinned[slot] or {}
         new_dev, new_pin = {}, {}
+        # device slots are allocated on the CONSUMER's stream (the caching allocator pools memory per stream: a slot
+        # allocated under the copy stream could not be recycled by the next feeder's, and every new feeder would
+        # cudaMalloc); the copy stream's writes into them are ordered by the freed/ready events
+        for k, t in batch.items():
+            if isinstance(t, torch.Tensor) and not t.is_cuda:
+                dev[k] = self._like(t, dev.get(k), device=self.device)
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(self._freed[slot])          # compute is done with this slot's previous batch
             for k, t in batch.items():
@@ -61,7 +67,7 @@ class DeviceFeeder:
                     p.copy_(t)
                     new_pin[k] = p
                     t = p
-                d = self._like(t, dev.get(k), device=self.device)
+                d = dev[k]
                 d.copy_(t, non_blocking=True)
                 self.h2d_bytes += t.numel() * t.element_size()
                 new_dev[k] = d
