@@ -9,8 +9,8 @@
 //   as MN-major operand (contraction over tokens)  : rows = K index, +2048 B per 16 tokens
 // so the same TMA tile serves both roles.
 //
-// forward  : CTA = (image, head, pair of 128-query tiles) ping-ponging on one stream of 128-key K/V blocks; two softmax
-//            warpgroups (thread = query row = TMEM lane) + MMA-issue warp + TMA-load warp, one CTA per SM.
+// forward  : CTA = (128 queries, head, image), 4 softmax warps (thread = query row = TMEM lane) + a control warp; four
+//            CTAs per SM (128 TMEM columns each) so one CTA's softmax overlaps the others' MMAs.
 // backward : CTA = (128 keys, head, image) loops over query blocks; Sᵀ and dPᵀ live in TMEM
 //            (lane = key), dV/dK accumulate in TMEM across the loop, dQ partials are reduced
 //            into an fp32 workspace with red.global.add.
@@ -67,42 +67,37 @@ __device__ __forceinline__ void store_row32_sw128(uint8_t* tile, int row, int co
 }
 
 // ============================================================================ forward
-// Work unit = (image, head, PAIR of 128-query tiles) — or the single left-over tile when the tile count is odd.
-// One CTA per SM runs a unit: both query tiles ping-pong on ONE stream of 128-key K/V blocks, so the tensor core
-// computes tile 1's scores (and the P·V of the previous block) while tile 0's softmax runs, and vice versa:
-//   warps 0-3 / 4-7 : softmax warpgroup of tile 0 / tile 1 (thread = query row = TMEM lane)
-//   warp 8          : MMA issue        warp 9 : TMA loads (Q tiles once, then a 3-deep ring of K and of V blocks)
-//   S_t  = Q_t·Kᵀ     SS-MMA, N = 128 keys (65 cycles per 16-wide k-step instead of 2 × 49 for two N = 64 MMAs)
-//   P_t  (bf16)       written to its own TMEM columns with tcgen05.st (two per 32-bit column).  P does not alias S:
-//                     the warpgroup releases S_t as soon as its last chunk sits in registers (≈ one chunk of math
-//                     before P_t is complete), so S_t of the NEXT block is computed while this block's softmax finishes
-//                     and the warpgroup never waits for the tensor core in steady state
-//   O_t += P_t·V      TS-MMA: A = P straight from TMEM, B = V rows from smem (MN-major); O_t stays in TMEM for the
-//                     whole key loop — no read-back per block, no P round trip through shared memory
-// TMEM columns (all 512): S0 [0,128)  S1 [128,256)  P0 [256,320)  P1 [320,384)  O0 [384,448)  O1 [448,512).
-// Epilogue: O_t/l → bf16 → the (now idle) Q_t tile in shared memory → one TMA store per tile (rows ≥ T clipped).
-// Softmax is single-pass with a lazily updated reference maximum: probabilities are taken relative to m_ref; whenever
-// a 32-column chunk exceeds it by more than 2^16 (always on the very first chunk, otherwise only for extreme logits)
-// everything accumulated so far is rescaled by 2^(old−new) ≤ 1 — exact bookkeeping, m_ref cancels in O/l and in the
-// LSE.  The last key block issues narrower MMAs (N, K rounded up to 16 valid keys) instead of computing masked
-// columns.  exp2 runs on the MUFU pipe (16/clk/SM — the unit that bounds this kernel at head_dim 64) except for
-// kPolyOf32 of every 32 elements, which take a Cody-Waite + degree-3 polynomial on the FMA pipe (relative error
-// 1.0e-4, below bf16's 3.9e-3 rounding of P).
-constexpr int kFwdWG = 128;                                // threads per softmax warpgroup
-constexpr int kFwdThreads = 2 * kFwdWG + 64;               // + MMA-issue warp + load warp
-constexpr int kKB = 128;                                   // keys per block
-constexpr int kStages = 3;
-constexpr int kFwdSmemQ = 0;                               // 2 × 16 KB
-constexpr int kFwdSmemK = kFwdSmemQ + 2 * kTileBytes;      // kStages × 16 KB
-constexpr int kFwdSmemV = kFwdSmemK + kStages * kTileBytes;
-constexpr int kFwdSmemBar = kFwdSmemV + kStages * kTileBytes;
-constexpr int kFwdSmemBytes = kFwdSmemBar + 256 + 1024;    // ≈ 129 KB
-constexpr int kFwdTmemCols = 512;
+// CTA = (128 queries, head, image); 4 softmax warps (thread = query row = TMEM lane) + 1 control warp
+// that owns TMA and MMA issue.  Four CTAs per SM: 16 softmax warps keep the MUFU pipe (16 exp2/clk/SM — the unit
+// that bounds attention at head_dim 64) fed while each CTA's own score → softmax → P·V chain waits on the tensor core.
+//   keys are consumed in sub-blocks of 64:
+//   S_u = Q·K_uᵀ       SS-MMA (N = 64) into the CTA's 64 score columns of TMEM
+//   P_u (bf16)         written back INTO the consumed S columns (two per 32-bit column) with tcgen05.st
+//   O += P_u·V_u       TS-MMA: A = P straight from TMEM, B = V rows from smem (MN-major); O accumulates
+//                      in TMEM across all sub-blocks — no per-block read-back, no P round trip via smem
+// Softmax is single-pass with a lazily updated reference maximum: probabilities are taken relative to
+// m_ref; whenever a 32-column chunk exceeds it by more than 2^16 (always on the first chunk, otherwise
+// only for extreme logits) everything accumulated so far is rescaled by 2^(old−new) ≤ 1 — exact
+// bookkeeping, m_ref cancels in O/l and in the LSE.  Probabilities are computed SPECULATIVELY against the current
+// reference while the chunk maximum is still being reduced (the MUFU pipe starts at once instead of after a 16-deep
+// max chain + vote); when the reference does move, the chunk is recomputed from the registers it still sits in.
+// The last sub-block issues narrower MMAs (N, K rounded up to 16 valid keys) instead of computing masked columns;
+// warps whose 32 query rows all lie beyond T (the padding of the last tile) skip the arithmetic.
+// Epilogue: O/l → bf16 → the (now idle) Q tile in shared memory → one TMA store (rows ≥ T clipped by the tensor map).
+// (A pair-of-tiles variant — two 128-query tiles ping-ponging on one 128-key K/V stream, N = 128 score MMAs, one CTA
+// of 8 softmax warps per SM — measured 60 µs against this kernel's 43: 2 softmax warps per scheduler cannot hide the
+// chunk latency, see DESIGN.md §4 and profiles/r02_attn_fwd_pair_timeline.txt.)
+constexpr int kFwdSoftmaxThreads = 128;
+constexpr int kFwdThreads = kFwdSoftmaxThreads + 32;
+constexpr int kSub = 64;                                   // keys per sub-block = one K/V TMA tile
+constexpr int kSubBytes = kSub * kDh * 2;                  // 8 KB
+constexpr int kFwdSmemQ = 0;
+constexpr int kFwdSmemK = kFwdSmemQ + kTileBytes;          // 2 buffers of 64 keys
+constexpr int kFwdSmemV = kFwdSmemK + 2 * kSubBytes;       // 2 buffers
+constexpr int kFwdSmemBar = kFwdSmemV + 2 * kSubBytes;
+constexpr int kFwdSmemBytes = kFwdSmemBar + 128 + 1024;    // ≈ 49 KB → four CTAs per SM
+constexpr int kFwdTmemCols = 128;  // S/P: [0,64)   O: [64,128)
 constexpr float kLazyMaxLog2 = 16.0f;
-#ifndef VITK_ATTN_POLY_OF32
-#define VITK_ATTN_POLY_OF32 0
-#endif
-constexpr int kPolyOf32 = VITK_ATTN_POLY_OF32;             // elements per 32 whose exp2 runs on the FMA pipe
 
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float r;
@@ -110,43 +105,11 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
   return r;
 }
 
-// 2^x for x ≤ ~16 on the FMA/ALU pipes: n = round(x) via the 1.5·2^23 trick, f = x − n ∈ [−½, ½],
-// 2^f ≈ 1 + f(c1 + f(c2 + f·c3)) (minimax, max relative error 1.01e-4), exponent patched in with an integer add.
-__device__ __forceinline__ float exp2_poly(float x) {
-  x = fmaxf(x, -125.0f);
-  const float t = x + 12582912.0f;
-  const float f = x - (t - 12582912.0f);
-  float p = fmaf(f, 0.05500865f, 0.24221093f);
-  p = fmaf(p, f, 0.69328299f);
-  p = fmaf(p, f, 1.0f);
-  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
-}
-
-template <int I>
-__device__ __forceinline__ float softmax_exp2(float x) {
-  if constexpr (kPolyOf32 > 0 && (I % 32) * kPolyOf32 / 32 != ((I % 32) + 1) * kPolyOf32 / 32) return exp2_poly(x);
-  return fast_exp2(x);
-}
-
-template <int I>
-__device__ __forceinline__ void softmax_pairs(const uint32_t (&r)[32], float scale_log2, float m_ref, float& rs0, float& rs1,
-                                              uint32_t (&pk)[16]) {
-  if constexpr (I < 16) {
-    const float p0 = softmax_exp2<2 * I>(fmaf(__uint_as_float(r[2 * I]), scale_log2, -m_ref));
-    const float p1 = softmax_exp2<2 * I + 1>(fmaf(__uint_as_float(r[2 * I + 1]), scale_log2, -m_ref));
-    rs0 += p0;
-    rs1 += p1;
-    pk[I] = pack_bf16x2(p0, p1);
-    softmax_pairs<I + 1>(r, scale_log2, m_ref, rs0, rs1, pk);
-  }
-}
-
-__global__ void __launch_bounds__(kFwdThreads, 1)
+__global__ void __launch_bounds__(kFwdThreads, 4)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_kv,
-                const __grid_constant__ CUtensorMap tma_o, float* __restrict__ lse, int T, int H, int BH, float scale_log2,
-                long long* tl) {
+                const __grid_constant__ CUtensorMap tma_o, float* __restrict__ lse, int T, int H, float scale_log2, long long* tl) {
   // tl (vitk_debug_timeline, ≥ 8192 int64): [3·cta + {0,1,2}] = globaltimer at entry / %smid / globaltimer at exit
-  const unsigned lin_cta = blockIdx.x;
+  const unsigned lin_cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
   if (tl != nullptr && threadIdx.x == 0 && lin_cta < 2000) {
     unsigned long long t; unsigned smid;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -159,301 +122,238 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
   uint8_t* sQ = smem + kFwdSmemQ;
   uint8_t* sK = smem + kFwdSmemK;
   uint8_t* sV = smem + kFwdSmemV;
-  uint64_t* bar_q = reinterpret_cast<uint64_t*>(smem + kFwdSmemBar);   // [2] Q tile landed
-  uint64_t* bar_k = bar_q + 2;                // [3] K block landed
-  uint64_t* bar_v = bar_k + kStages;          // [3] V block landed
-  uint64_t* bar_kfree = bar_v + kStages;      // [3] every S MMA reading this K block retired
-  uint64_t* bar_vfree = bar_kfree + kStages;  // [3] every P·V MMA reading this V block retired
-  uint64_t* bar_s = bar_vfree + kStages;      // [2] S_t ready
-  uint64_t* bar_p = bar_s + 2;                // [2] P_t written by the 4 warps of warpgroup t
-  uint64_t* bar_pv = bar_p + 2;               // [2] P·V_t of a block retired (only the rescale path waits on it)
-  uint64_t* bar_o = bar_pv + 2;               // [2] last P·V_t retired
-  uint64_t* bar_sfree = bar_o + 2;            // [2] S_t of the current block fully read into registers by warpgroup t
-  constexpr int kNumBars = 2 + 4 * kStages + 10;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_q + kNumBars);
+  uint64_t* bar_q = reinterpret_cast<uint64_t*>(smem + kFwdSmemBar);
+  uint64_t* bar_k = bar_q + 1;      // [2] K tile landed
+  uint64_t* bar_v = bar_q + 3;      // [2] V tile landed
+  uint64_t* bar_free = bar_q + 5;   // [2] K/V buffer consumed by its P·V
+  uint64_t* bar_s = bar_q + 7;      // S ready
+  uint64_t* bar_p = bar_q + 8;      // P written by the 4 softmax warps
+  uint64_t* bar_o = bar_q + 9;      // last P·V retired
+  uint64_t* bar_pv = bar_q + 10;    // P·V(u) retired (phase u): only the rescale path waits on it
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_q + 11);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  // unit → (image·head, first tile, number of tiles): pair units first (they cost twice a single), singles last
-  const int ntile = (T + kTile - 1) / kTile, npair = ntile >> 1;
-  int bh, tile0, ntl;
-  {
-    const int u = blockIdx.x, n_pair_units = BH * npair;
-    if (u < n_pair_units) { bh = u / npair; tile0 = 2 * (u - bh * npair); ntl = 2; }
-    else { bh = u - n_pair_units; tile0 = ntile - 1; ntl = 1; }
-  }
-  const int b = bh / H, h = bh - b * H;
-  const int nblk = (T + kKB - 1) / kKB;
+  const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int nsub = (T + kSub - 1) / kSub;
   const int colq = h * kDh, colk = (H + h) * kDh, colv = (2 * H + h) * kDh;
 
   if (tid == 0) {
     tma_prefetch_desc(&tma_q);
     tma_prefetch_desc(&tma_kv);
     tma_prefetch_desc(&tma_o);
-    for (int i = 0; i < kNumBars; ++i)
-      mbar_init(bar_q + i, ((bar_q + i >= bar_p && bar_q + i < bar_pv) || bar_q + i >= bar_sfree) ? 4 : 1);
+    for (int i = 0; i < 11; ++i) mbar_init(bar_q + i, i == 8 ? 4 : 1);
     fence_mbar_init();
   }
-  if (warp == 8) tmem_alloc(tmem_slot, kFwdTmemCols);
+  if (warp == 4) tmem_alloc(tmem_slot, kFwdTmemCols);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   pdl_wait();
   pdl_launch_dependents();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // broadcast marks it warp-uniform: no per-MMA elect-broadcast-retry loop
-  if (warp == 0) VITK_FSTAMP(200);                                    // prologue done (clock64, CTA 0)
+  const uint32_t tmem_o = tmem_base + 64;
 
-  if (warp == 9) {
-    // ------------------------------------------------------------------ load warp
-    if (elect_one()) {
-      for (int t = 0; t < ntl; ++t) {
-        mbar_arrive_expect_tx(&bar_q[t], kTileBytes);
-        tma_load_3d(sQ + t * kTileBytes, &tma_q, &bar_q[t], colq, (tile0 + t) * kTile, b);
-      }
-    }
-    for (int j = 0; j < nblk; ++j) {
-      const int st = j % kStages;
-      const uint32_t ph = ((j / kStages) - 1) & 1;
-      if (j >= kStages) mbar_wait(&bar_kfree[st], ph);
-      if (elect_one()) {
-        mbar_arrive_expect_tx(&bar_k[st], kTileBytes);
-        tma_load_3d(sK + st * kTileBytes, &tma_kv, &bar_k[st], colk, j * kKB, b);
-      }
-      if (j >= kStages) mbar_wait(&bar_vfree[st], ph);
-      if (elect_one()) {
-        mbar_arrive_expect_tx(&bar_v[st], kTileBytes);
-        tma_load_3d(sV + st * kTileBytes, &tma_kv, &bar_v[st], colv, j * kKB, b);
-      }
-    }
-    __syncwarp();
-  } else if (warp == 8) {
-    // ------------------------------------------------------------------ MMA-issue warp
+  if (warp == 4) {
+    // ------------------------------------------------------------------ control warp: TMA + MMA issue
     // Every lane runs this loop so that descriptors and addresses stay warp-uniform (uniform registers), and the
-    // issuing instructions sit under elect.sync: ptxas then emits back-to-back UTCHMMA on uniform registers.
-    constexpr uint32_t kTile16 = kTileBytes >> 4;
-    const uint64_t q_desc = umma_smem_desc(smem_u32(sQ), 0, 1024);
-    const uint64_t k_desc = umma_smem_desc(smem_u32(sK), 0, 1024);
-    const uint64_t v_desc = umma_smem_desc(smem_u32(sV), kTileBytes, 1024);
-    constexpr uint32_t idesc_pv = umma_idesc_bf16(kTile, kDh, 0, 1);
-    auto blk_cols = [&](int j) { return (min(kKB, T - j * kKB) + 15) & ~15; };   // keys block j needs
-    auto issue_s = [&](int t, int j) {        // S_t(j) = Q_t·K(j)ᵀ
-      const uint64_t bk = k_desc + static_cast<uint64_t>((j % kStages) * kTile16);
-      const uint64_t aq = q_desc + static_cast<uint64_t>(t * kTile16);
-      const uint32_t idesc_s = umma_idesc_bf16(kTile, blk_cols(j), 0, 0);
-      if (elect_one()) {
-#pragma unroll
-        for (int k = 0; k < kDh / 16; ++k) tc_mma_bf16(tmem_base + t * 128, aq + 2 * k, bk + 2 * k, idesc_s, k > 0);
-        tc_commit(&bar_s[t]);
-        if (t == ntl - 1) tc_commit(&bar_kfree[j % kStages]);
-      }
-    };
-    mbar_wait(&bar_k[0], 0);
-    for (int t = 0; t < ntl; ++t) {
-      mbar_wait(&bar_q[t], 0);
-      tc_fence_after_sync();
-      issue_s(t, 0);
-    }
-    for (int j = 0; j < nblk; ++j) {
-      const int st = j % kStages;
-      const uint32_t ph = (j / kStages) & 1;
-      const int ksteps = blk_cols(j) / 16;
-      const uint64_t bv = v_desc + static_cast<uint64_t>(st * kTile16);
-      mbar_wait(&bar_v[st], ph);
-      if (j + 1 < nblk) mbar_wait(&bar_k[(j + 1) % kStages], ((j + 1) / kStages) & 1);
-      for (int t = 0; t < ntl; ++t) {
-        if (j + 1 < nblk) {                     // S_t(j+1) as soon as warpgroup t holds all of S_t(j) in registers
-          VITK_FSTAMP(16 * j + 8 + 3 * t + 0);
-          mbar_wait(&bar_sfree[t], j & 1);
-          tc_fence_after_sync();
-          issue_s(t, j + 1);
-        }
-        mbar_wait(&bar_p[t], j & 1);
-        tc_fence_after_sync();
-        VITK_FSTAMP(16 * j + 8 + 3 * t + 1);                      // got P_t(j)
-        const uint32_t tm_p = tmem_base + 256 + t * 64, tm_o = tmem_base + 384 + t * kDh;
+    // issuing instructions sit under elect.sync: ptxas then knows exactly one lane issues and emits back-to-back
+    // UTCHMMA / UTMALDG on uniform registers.  Under a lane-id test (`lane == 0`) every MMA is wrapped in an
+    // elect/broadcast/retry loop costing ≈100 cycles — several times the 49 cycles an N = 64 MMA occupies the pipe.
+    {
+      auto load_kv = [&](int u) {
+        const int buf = u & 1;
         if (elect_one()) {
-          if (ksteps == kKB / 16) {             // full block: unrolled, MMAs issue back to back
+          mbar_arrive_expect_tx(&bar_k[buf], kSubBytes);
+          tma_load_3d(sK + buf * kSubBytes, &tma_kv, &bar_k[buf], colk, u * kSub, b);
+          mbar_arrive_expect_tx(&bar_v[buf], kSubBytes);
+          tma_load_3d(sV + buf * kSubBytes, &tma_kv, &bar_v[buf], colv, u * kSub, b);
+        }
+      };
+      if (elect_one()) {
+        mbar_arrive_expect_tx(bar_q, kTileBytes);
+        tma_load_3d(sQ, &tma_q, bar_q, colq, qb * kTile, b);
+      }
+      load_kv(0);
+      if (nsub > 1) load_kv(1);
+      const uint64_t q_desc = umma_smem_desc(smem_u32(sQ), 0, 1024);
+      const uint64_t k_desc = umma_smem_desc(smem_u32(sK), 0, 1024);
+      const uint64_t v_desc = umma_smem_desc(smem_u32(sV), kSubBytes, 1024);
+      auto sub_cols = [&](int u) { return (min(kSub, T - u * kSub) + 15) & ~15; };   // keys sub-block u needs
+      auto issue_s = [&](int u) {
+        const int buf = u & 1;
+        mbar_wait(&bar_k[buf], (u >> 1) & 1);
+        tc_fence_after_sync();
+        const uint64_t bk = k_desc + static_cast<uint64_t>(buf * (kSubBytes >> 4));
+        const uint32_t idesc_s = umma_idesc_bf16(kTile, sub_cols(u), 0, 0);
+        if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < kKB / 16; ++k)
-              tc_mma_bf16_ts(tm_o, tm_p + k * 8, bv + k * 128, idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < kDh / 16; ++k) tc_mma_bf16(tmem_base, q_desc + 2 * k, bk + 2 * k, idesc_s, k > 0);
+          tc_commit(bar_s);
+        }
+      };
+      mbar_wait(bar_q, 0);
+      issue_s(0);
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(kTile, kDh, 0, 1);
+      for (int u = 0; u < nsub; ++u) {
+        const int buf = u & 1;
+        const uint32_t ph = (u >> 1) & 1;
+        mbar_wait(&bar_v[buf], ph);
+        mbar_wait(bar_p, u & 1);
+        tc_fence_after_sync();
+        const uint64_t bv = v_desc + static_cast<uint64_t>(buf * (kSubBytes >> 4));
+        const int ksteps = sub_cols(u) / 16;
+        if (elect_one()) {
+          if (ksteps == kSub / 16) {           // full sub-block: unrolled, MMAs issue back to back
+#pragma unroll
+            for (int k = 0; k < kSub / 16; ++k)
+              tc_mma_bf16_ts(tmem_o, tmem_base + k * 8, bv + k * 128, idesc_pv, (u > 0 || k > 0) ? 1u : 0u);
           } else {
             for (int k = 0; k < ksteps; ++k)
-              tc_mma_bf16_ts(tm_o, tm_p + k * 8, bv + k * 128, idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+              tc_mma_bf16_ts(tmem_o, tmem_base + k * 8, bv + k * 128, idesc_pv, (u > 0 || k > 0) ? 1u : 0u);
           }
-          tc_commit(&bar_pv[t]);
-          if (t == ntl - 1) tc_commit(&bar_vfree[st]);
-          if (j == nblk - 1) tc_commit(&bar_o[t]);
+          tc_commit(bar_pv);
+          tc_commit(&bar_free[buf]);
+          if (u == nsub - 1) tc_commit(bar_o);
         }
-        VITK_FSTAMP(16 * j + 8 + 3 * t + 2);                      // S_t(j+1), P·V_t(j) issued
+        if (u + 1 < nsub) issue_s(u + 1);     // queued right behind P·V(u): MMAs retire in issue order
+        if (u + 2 < nsub) {                   // refill this K/V buffer once its P·V has retired
+          mbar_wait(&bar_free[buf], ph);
+          load_kv(u + 2);
+        }
       }
     }
     __syncwarp();
   } else {
-    // ------------------------------------------------------------------ softmax warpgroups
-    const int t = warp >> 2;                  // tile of this warpgroup
-    if (t < ntl) {
-      const int row = tid - t * kFwdWG;       // query row inside the tile = TMEM lane
-      const uint32_t lane_field = static_cast<uint32_t>((warp & 3) * 32) << 16;
-      const uint32_t tm_s = tmem_base + lane_field + t * 128;
-      const uint32_t tm_p = tmem_base + lane_field + 256 + t * 64;
-      const uint32_t tm_o = tmem_base + lane_field + 384 + t * kDh;
-      bool p_free = true;                     // P·V_t of the previous block has finished reading the P columns
-      float m_ref = -INFINITY, l_run = 0.f;
-      for (int j = 0; j < nblk; ++j) {
-        const int nvalid = min(kKB, T - j * kKB);
-        const int nchunk = (nvalid + 31) >> 5;
-        if ((warp & 3) == 0) VITK_FSTAMP(16 * j + 4 * t + 0);      // waiting for S_t(j)
-        mbar_wait(&bar_s[t], j & 1);
-        tc_fence_after_sync();
-        if ((warp & 3) == 0) VITK_FSTAMP(16 * j + 4 * t + 1);      // S_t(j) ready
-        float rs0 = 0.f, rs1 = 0.f;
-        // one 32-column chunk of the row: lazy-maximum bookkeeping, exp2, bf16 pack, P written over consumed S columns
-        auto chunk = [&](uint32_t (&r)[32], int c) {
-          const bool full = (c + 1) * 32 <= nvalid;
-          // Probabilities are computed SPECULATIVELY against the current reference maximum while the chunk maximum is
-          // being reduced (two independent instruction streams: the MUFU pipe starts at once instead of after a
-          // 16-deep max chain + vote); the reference moves only on the first chunk of a row and for extreme logits,
-          // and then the chunk is simply recomputed from the registers it still sits in.
-          uint32_t pk[16];
-          float s0 = 0.f, s1 = 0.f;
-          float cm = -INFINITY;
-          if (full) {
-            softmax_pairs<0>(r, scale_log2, m_ref, s0, s1, pk);
+    // ------------------------------------------------------------------ softmax warps
+    const uint32_t lane_field = static_cast<uint32_t>(warp * 32) << 16;
+    float m_ref = -INFINITY, l_run = 1.f;
+    const bool live = qb * kTile + warp * 32 < T;     // false: all 32 query rows of this warp are padding beyond T
+    if (live) l_run = 0.f;
+    for (int u = 0; u < nsub; ++u) {
+      const int nvalid = min(kSub, T - u * kSub);
+      const int nchunk = (nvalid + 31) >> 5;
+      const uint32_t tm_s = tmem_base + lane_field;
+      mbar_wait(bar_s, u & 1);
+      tc_fence_after_sync();
+      float rs0 = 0.f, rs1 = 0.f;
+      for (int c = 0; live && c < nchunk; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(tm_s + c * 32, r);
+        tmem_ld_wait();
+        const bool full = (c + 1) * 32 <= nvalid;
+        uint32_t pk[16];
+        float s0 = 0.f, s1 = 0.f;
+        float cm = -INFINITY;
+        if (full) {
 #pragma unroll
-            for (int i = 0; i < 32; i += 2) cm = fmax3(cm, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (c * 32 + i < nvalid) cm = fmaxf(cm, __uint_as_float(r[i]));
+          for (int i = 0; i < 16; ++i) {          // speculative: against the reference maximum as it stands
+            const float p0 = fast_exp2(fmaf(__uint_as_float(r[2 * i]), scale_log2, -m_ref));
+            const float p1 = fast_exp2(fmaf(__uint_as_float(r[2 * i + 1]), scale_log2, -m_ref));
+            s0 += p0;
+            s1 += p1;
+            pk[i] = pack_bf16x2(p0, p1);
           }
-          const float m_c = cm * scale_log2;
-          const bool fix = m_c > m_ref + kLazyMaxLog2;
-          const bool moved = __any_sync(0xffffffffu, fix);
-          if (moved) {
-            const float m_new = fix ? m_c : m_ref;
-            const float alpha = fix ? fast_exp2(m_ref - m_new) : 1.0f;
-            l_run *= alpha;
-            rs0 *= alpha;
-            rs1 *= alpha;
-            tmem_ld_wait();                         // a prefetched chunk may be in flight: let it land first
-            tmem_st_wait();                         // P chunks of this block written so far
-            if (j > 0) {
-              // O_t holds P·V of blocks < j; P·V_t(j-1) may still be in flight
-              if (!p_free) {
-                mbar_wait(&bar_pv[t], (j - 1) & 1);
-                tc_fence_after_sync();
-                p_free = true;
-              }
-#pragma unroll 1
-              for (int cc = 0; cc < 2; ++cc) {
-                uint32_t ro[32];
-                tmem_ld_32x32(tm_o + cc * 32, ro);
-                tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) ro[i] = __float_as_uint(__uint_as_float(ro[i]) * alpha);
-                tmem_st_32x32(tm_o + cc * 32, ro);
-              }
-            }
+          for (int i = 0; i < 32; i += 2) cm = fmax3(cm, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i < nvalid) cm = fmaxf(cm, __uint_as_float(r[i]));
+        }
+        const float m_c = cm * scale_log2;
+        const bool fix = m_c > m_ref + kLazyMaxLog2;
+        const bool moved = __any_sync(0xffffffffu, fix);
+        if (moved) {
+          const float m_new = fix ? m_c : m_ref;
+          const float alpha = fix ? fast_exp2(m_ref - m_new) : 1.0f;
+          l_run *= alpha;
+          rs0 *= alpha;
+          rs1 *= alpha;
+          if (u > 0) {
+            // O holds P·V of sub-blocks < u; P·V(u-1) may still be in flight
+            mbar_wait(bar_pv, (u - 1) & 1);
+            tc_fence_after_sync();
 #pragma unroll 1
-            for (int cc = 0; cc < c; ++cc) {        // P chunks of this block already written
-              uint32_t pq[16];
-              tmem_ld_32x16(tm_p + cc * 16, pq);
+            for (int cc = 0; cc < 2; ++cc) {
+              uint32_t ro[32];
+              tmem_ld_32x32(tmem_o + lane_field + cc * 32, ro);
               tmem_ld_wait();
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pq[i]));
-                pq[i] = pack_bf16x2(f.x * alpha, f.y * alpha);
-              }
-              tmem_st_32x16(tm_p + cc * 16, pq);
+              for (int i = 0; i < 32; ++i) ro[i] = __float_as_uint(__uint_as_float(ro[i]) * alpha);
+              tmem_st_32x32(tmem_o + lane_field + cc * 32, ro);
             }
-            m_ref = m_new;
           }
-          if (moved || !full) {
-            s0 = s1 = 0.f;
+          tmem_st_wait();
+#pragma unroll 1
+          for (int cc = 0; cc < c; ++cc) {
+            uint32_t pq[16];
+            tmem_ld_32x16(tm_s + cc * 16, pq);
+            tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              float p0 = fast_exp2(fmaf(__uint_as_float(r[2 * i]), scale_log2, -m_ref));
-              float p1 = fast_exp2(fmaf(__uint_as_float(r[2 * i + 1]), scale_log2, -m_ref));
-              if (c * 32 + 2 * i >= nvalid) p0 = 0.f;
-              if (c * 32 + 2 * i + 1 >= nvalid) p1 = 0.f;
-              s0 += p0;
-              s1 += p1;
-              pk[i] = pack_bf16x2(p0, p1);
+              const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pq[i]));
+              pq[i] = pack_bf16x2(f.x * alpha, f.y * alpha);
             }
+            tmem_st_32x16(tm_s + cc * 16, pq);
           }
-          rs0 += s0;
-          rs1 += s1;
-          if (!p_free) {                        // first P chunk of this block: P·V_t(j-1) must be done with the P columns
-            mbar_wait(&bar_pv[t], (j - 1) & 1);
-            tc_fence_after_sync();
-            p_free = true;
-          }
-          tmem_st_32x16(tm_p + c * 16, pk);     // chunk c of P → P columns [16c, 16c+16)
-        };
-        auto release_s = [&]() {                // every lane of this warp has its part of S_t(j) in registers
-          tc_fence_before_sync();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&bar_sfree[t]);
-        };
-        // two register buffers: the next chunk's TMEM load is in flight during this chunk's math
-        uint32_t ra[32], rb[32];
-        tmem_ld_32x32(tm_s, ra);
-        for (int c = 0; c < nchunk; c += 2) {
-          tmem_ld_wait();
-          tmem_regs_ready(ra);
-          if (c + 1 < nchunk) tmem_ld_32x32(tm_s + (c + 1) * 32, rb); else release_s();
-          chunk(ra, c);
-          if (c + 1 < nchunk) {
-            tmem_ld_wait();
-            tmem_regs_ready(rb);
-            if (c + 2 < nchunk) tmem_ld_32x32(tm_s + (c + 2) * 32, ra); else release_s();
-            chunk(rb, c + 1);
+          m_ref = m_new;
+        }
+        if (moved || !full) {                       // the reference moved (or a ragged chunk): (re)compute from r
+          s0 = s1 = 0.f;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float p0 = fast_exp2(fmaf(__uint_as_float(r[2 * i]), scale_log2, -m_ref));
+            float p1 = fast_exp2(fmaf(__uint_as_float(r[2 * i + 1]), scale_log2, -m_ref));
+            if (c * 32 + 2 * i >= nvalid) p0 = 0.f;
+            if (c * 32 + 2 * i + 1 >= nvalid) p1 = 0.f;
+            s0 += p0;
+            s1 += p1;
+            pk[i] = pack_bf16x2(p0, p1);
           }
         }
-        p_free = false;
-        l_run += rs0 + rs1;
-        if ((warp & 3) == 0) VITK_FSTAMP(16 * j + 4 * t + 2);      // math done
-        tmem_st_wait();
-        tc_fence_before_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_p[t]);
-        if ((warp & 3) == 0) VITK_FSTAMP(16 * j + 4 * t + 3);      // P_t(j) published
+        rs0 += s0;
+        rs1 += s1;
+        tmem_st_32x16(tm_s + c * 16, pk);     // P overwrites S columns already consumed
       }
-      mbar_wait(&bar_o[t], 0);
-      tc_fence_after_sync();
-      if ((warp & 3) == 0) VITK_FSTAMP(201 + 2 * t);                  // last P·V_t retired
-      const int tq = (tile0 + t) * kTile + row;
-      const float inv = 1.0f / l_run;
-      // O_t / l → bf16 → Q_t's shared-memory tile (every S_t MMA that read it has retired), 128-byte swizzled rows
-      uint8_t* srow = sQ + t * kTileBytes + row * 128;
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t ro[32];
-        tmem_ld_32x32(tm_o + c * 32, ro);
-        tmem_ld_wait();
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint4 w;
-          w.x = pack_bf16x2(__uint_as_float(ro[8 * q + 0]) * inv, __uint_as_float(ro[8 * q + 1]) * inv);
-          w.y = pack_bf16x2(__uint_as_float(ro[8 * q + 2]) * inv, __uint_as_float(ro[8 * q + 3]) * inv);
-          w.z = pack_bf16x2(__uint_as_float(ro[8 * q + 4]) * inv, __uint_as_float(ro[8 * q + 5]) * inv);
-          w.w = pack_bf16x2(__uint_as_float(ro[8 * q + 6]) * inv, __uint_as_float(ro[8 * q + 7]) * inv);
-          *reinterpret_cast<uint4*>(srow + (((4 * c + q) ^ (row & 7)) << 4)) = w;
-        }
-      }
-      fence_proxy_async_smem();
-      asm volatile("bar.sync %0, %1;" ::"r"(1 + t), "r"(kFwdWG) : "memory");
-      if (row == 0) {
-        tma_store_3d(&tma_o, sQ + t * kTileBytes, colq, (tile0 + t) * kTile, b);
-        tma_store_commit();
-        tma_store_wait_read<0>();
-      }
-      if (tq < T) lse[(static_cast<long long>(b) * H + h) * T + tq] = (m_ref + log2f(l_run)) * kLn2;
-      if ((warp & 3) == 0) VITK_FSTAMP(202 + 2 * t);                  // O_t stored
+      l_run += rs0 + rs1;
+      tmem_st_wait();
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_p);
     }
+    mbar_wait(bar_o, 0);
+    tc_fence_after_sync();
+    const int t = qb * kTile + tid;
+    const float inv = 1.0f / l_run;
+    // O / l → bf16 → the Q tile's shared memory (every S MMA that read it has retired), 128-byte swizzled rows
+    uint8_t* srow = sQ + tid * 128;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_o + lane_field + c * 32, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint4 w;
+        w.x = pack_bf16x2(__uint_as_float(r[8 * q + 0]) * inv, __uint_as_float(r[8 * q + 1]) * inv);
+        w.y = pack_bf16x2(__uint_as_float(r[8 * q + 2]) * inv, __uint_as_float(r[8 * q + 3]) * inv);
+        w.z = pack_bf16x2(__uint_as_float(r[8 * q + 4]) * inv, __uint_as_float(r[8 * q + 5]) * inv);
+        w.w = pack_bf16x2(__uint_as_float(r[8 * q + 6]) * inv, __uint_as_float(r[8 * q + 7]) * inv);
+        *reinterpret_cast<uint4*>(srow + (((4 * c + q) ^ (tid & 7)) << 4)) = w;
+      }
+    }
+    fence_proxy_async_smem();
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (tid == 0) {
+      tma_store_3d(&tma_o, sQ, colq, qb * kTile, b);
+      tma_store_commit();
+      tma_store_wait_read<0>();
+    }
+    if (t < T) lse[(static_cast<long long>(b) * H + h) * T + t] = (m_ref + log2f(l_run)) * kLn2;
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == 4) {
     tc_fence_after_sync();
     tmem_dealloc(tmem_base, kFwdTmemCols);
   }
@@ -849,20 +749,18 @@ extern "C" VITK_API int vitk_attn_fwd(const void* qkv, int64_t B, int64_t T, int
   if (int rc = check_shape("attn_fwd", B, T, H)) return rc;
   VITK_REQUIRE(aligned16(qkv) && aligned16(o), VITK_EALIGN, "attn_fwd: buffers must be 16-byte aligned");
   VITK_REQUIRE(scale > 0.f, VITK_EINVAL, "attn_fwd: scale must be positive");
-  CUtensorMap tm, tm_o;      // one box shape (128 rows × 64 columns) serves Q tiles, K/V blocks and the O store
+  CUtensorMap tm, tm_kv, tm_o;
   if (int rc = qkv_tensor_map(&tm, qkv, B, T, 3 * H * kDh)) return rc;
+  if (int rc = qkv_tensor_map(&tm_kv, qkv, B, T, 3 * H * kDh, kSub)) return rc;
   if (int rc = qkv_tensor_map(&tm_o, o, B, T, H * kDh)) return rc;
   static std::atomic<int> attr_done{0};
   if (!attr_done.load()) {
     VITK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmemBytes));
     attr_done.store(1);
   }
-  const int64_t ntile = (T + kTile - 1) / kTile;
-  const int64_t units = B * H * ((ntile >> 1) + (ntile & 1));
-  VITK_REQUIRE(units < (1LL << 31), VITK_EINVAL, "attn_fwd: too many work units");
-  VITK_CUDA(launch_pdl(attn_fwd_kernel, dim3(static_cast<unsigned>(units)), dim3(kFwdThreads), kFwdSmemBytes,
-                       static_cast<cudaStream_t>(stream), tm, tm, tm_o, lse, static_cast<int>(T),
-                       static_cast<int>(H), static_cast<int>(B * H), scale * kLog2e, g_timeline));
+  const dim3 grid(static_cast<unsigned>((T + kTile - 1) / kTile), static_cast<unsigned>(H), static_cast<unsigned>(B));
+  VITK_CUDA(launch_pdl(attn_fwd_kernel, grid, dim3(kFwdThreads), kFwdSmemBytes, static_cast<cudaStream_t>(stream), tm, tm_kv,
+                       tm_o, lse, static_cast<int>(T), static_cast<int>(H), scale * kLog2e, g_timeline));
   VITK_LAUNCH_CHECK("attn_fwd_kernel");
   return 0;
 }

@@ -20,7 +20,7 @@ ops.attn_fwd(qkv, B, T, H, 0.125, o=o, lse=lse)
 torch.cuda.synchronize()
 pkg._lib.lib().vitk_debug_timeline(None)
 t = tl.cpu().tolist()
-n = 3 * H * B          # 2 pair units + 1 single unit per (image, head)
+n = 5 * H * B
 rec = [(t[3 * i], t[3 * i + 1], t[3 * i + 2]) for i in range(n)]
 t0 = min(r[0] for r in rec)
 end = max(r[2] for r in rec)
@@ -38,14 +38,3 @@ starts = sorted((r[0] - t0) / 1e3 for r in rec)
 print("entry times us (every 60th CTA):", [round(x, 1) for x in starts[::60]])
 sm0 = sorted(per_sm[rec[0][1]])
 print("CTAs on the SM of CTA 0 (entry, exit us):", [(round(a, 1), round(b, 1)) for a, b in sm0])
-
-# ---- CTA 0 (a pair unit): clock64 stamps per key block, relative to "prologue done"
-base = 6000
-z = t[base + 200]
-print("CTA 0, cycles since prologue done; per key block j:")
-print("  j | WG0: wait S  got S  math done  P pub | WG1: wait S  got S  math done  P pub | MMA: wait P0  got P0  issued | wait P1  got P1  issued")
-for j in range(5):
-    v = [t[base + 16 * j + k] - z for k in range(14)]
-    print(f"  {j} | " + " ".join(f"{x:8d}" for x in v[0:4]) + " | " + " ".join(f"{x:8d}" for x in v[4:8]) + " | " +
-          " ".join(f"{x:8d}" for x in v[8:11]) + " | " + " ".join(f"{x:8d}" for x in v[11:14]))
-print("  last P.V retired / O stored: tile 0", t[base + 201] - z, t[base + 202] - z, " tile 1", t[base + 203] - z, t[base + 204] - z)
