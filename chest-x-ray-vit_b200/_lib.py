@@ -61,7 +61,8 @@ _PROTOS = {
     "vitk_fill_zero": (C.c_int, [_p, _sz, _p]),
     "vitk_adamw": (C.c_int, [_p, _p, _p, _p, _p, _i64, _f, _f, _f, _f, _f, _f, _f, _p, C.c_int, _p, _p]),
     "vitk_adamw_tick": (C.c_int, [_p, C.c_int, _f, _f, _p, _p]),
-    "vitk_sumsq_f32": (C.c_int, [_p, _i64, _p, _p]),
+    "vitk_sumsq_f32": (C.c_int, [_p, _i64, _p, _p, _p]),
+    "vitk_sumsq_scratch_floats": (C.c_int64, []),
     "vitk_clip_scale": (C.c_int, [_p, _f, _p, _p]),
     "vitk_launch_count": (C.c_int64, []),
     "vitk_gemm_plan": (C.c_int, [C.POINTER(GemmArgs), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),

@@ -42,8 +42,16 @@ adamw_kernel(float4* __restrict__ p, float4* __restrict__ g, float4* __restrict_
   }
 }
 
-__global__ void __launch_bounds__(256) sumsq_kernel(const float4* __restrict__ x, long long n4, float* __restrict__ out) {
+// Σ x² in a FIXED summation order: every block writes its partial sum to scratch[2 + block], takes a ticket, and the
+// block that draws the last ticket adds the partials up in index order and accumulates the total into *out.  The result
+// does not depend on which block finishes last, so data-parallel replicas that hold bit-identical gradients compute
+// bit-identical clip coefficients and their parameters never drift apart (an atomicAdd per block would make the
+// coefficient — hence every parameter — depend on the order of the atomics).  scratch[0] is the ticket counter
+// (left at zero), scratch[1] is unused padding.
+__global__ void __launch_bounds__(256) sumsq_kernel(const float4* __restrict__ x, long long n4, float* __restrict__ out,
+                                                    float* __restrict__ scratch) {
   __shared__ float red[8];
+  __shared__ bool is_last;
   float s = 0.f;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -57,7 +65,25 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float4* __restrict__ x
   if (threadIdx.x == 0) {
     float t = 0.f;
     for (int w = 0; w < 8; ++w) t += red[w];
-    atomicAdd(out, t);
+    scratch[2 + blockIdx.x] = t;
+    __threadfence();
+    const unsigned ticket = atomicInc(reinterpret_cast<unsigned*>(scratch), gridDim.x - 1);   // wraps to 0 after the last block
+    is_last = ticket == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  // fixed-order tree over the partials: thread t sums partials t, t+256, … in order, then a fixed shuffle/smem tree
+  float t = 0.f;
+  for (unsigned i = threadIdx.x; i < gridDim.x; i += 256) t += __ldcg(scratch + 2 + i);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = t;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int w = 0; w < 8; ++w) tot += red[w];
+    *out += tot;
   }
 }
 
@@ -110,14 +136,16 @@ extern "C" VITK_API int vitk_adamw_tick(int64_t* step_dev, int increment, float 
   return 0;
 }
 
-extern "C" VITK_API int vitk_sumsq_f32(const float* x, int64_t n, float* out, vitk_stream_t stream) {
-  VITK_REQUIRE(x && out && n > 0 && n % 4 == 0 && aligned16(x), VITK_EINVAL, "sumsq: n must be a positive multiple of 4");
+extern "C" VITK_API int64_t vitk_sumsq_scratch_floats(void) { return 2 + static_cast<int64_t>(num_sms()) * 8; }
+
+extern "C" VITK_API int vitk_sumsq_f32(const float* x, int64_t n, float* out, float* scratch, vitk_stream_t stream) {
+  VITK_REQUIRE(x && out && scratch && n > 0 && n % 4 == 0 && aligned16(x), VITK_EINVAL, "sumsq: n must be a positive multiple of 4");
   const long long n4 = n / 4;
   long long blocks = (n4 + 255) / 256;
   const long long cap = static_cast<long long>(num_sms()) * 8;
   if (blocks > cap) blocks = cap;
   sumsq_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const float4*>(x), n4, out);
+      reinterpret_cast<const float4*>(x), n4, out, scratch);
   VITK_LAUNCH_CHECK("sumsq_kernel");
   return 0;
 }

@@ -232,8 +232,17 @@ def adamw_tick(step_dev: torch.Tensor, increment: bool, beta1: float, beta2: flo
                "adamw_tick")
 
 
-def sumsq(x: torch.Tensor, out: torch.Tensor):
-    _lib.check(_lib.lib().vitk_sumsq_f32(x.data_ptr(), x.numel(), out.data_ptr(), _stream()), "sumsq_f32")
+_sumsq_scratch = {}
+
+
+def sumsq(x: torch.Tensor, out: torch.Tensor, scratch: Optional[torch.Tensor] = None):
+    """out[0] += Σ x², in a fixed summation order (bit-reproducible).  ``scratch``: zero-initialised fp32 buffer of
+    ``vitk_sumsq_scratch_floats()`` elements; one per device is kept here when none is given."""
+    if scratch is None:
+        scratch = _sumsq_scratch.get(x.device)
+        if scratch is None:
+            scratch = _sumsq_scratch[x.device] = torch.zeros(int(_lib.lib().vitk_sumsq_scratch_floats()), dtype=f32, device=x.device)
+    _lib.check(_lib.lib().vitk_sumsq_f32(x.data_ptr(), x.numel(), out.data_ptr(), scratch.data_ptr(), _stream()), "sumsq_f32")
 
 
 def clip_scale(sumsq_t: torch.Tensor, max_norm: float, scale: torch.Tensor):

@@ -36,6 +36,7 @@ class VitkAdamW(torch.optim.Optimizer):
         self._m, self._v = torch.zeros_like(flat), torch.zeros_like(flat)
         self._ss = torch.zeros(1, dtype=torch.float32, device=flat.device)
         self._scale = torch.ones(1, dtype=torch.float32, device=flat.device)
+        self._ss_scratch = torch.zeros(int(ops._lib.lib().vitk_sumsq_scratch_floats()), dtype=torch.float32, device=flat.device)
 
     def _segments(self, active):
         """Contiguous [start, end) ranges of the flat buffer to update, split at the gemm / decay / no-decay
@@ -97,10 +98,10 @@ class VitkAdamW(torch.optim.Optimizer):
         if self.max_grad_norm is not None:
             ops.fill_zero(self._ss)
             if whole:
-                ops.sumsq(g, self._ss)
+                ops.sumsq(g, self._ss, self._ss_scratch)
             else:
                 for a, b, _, _ in segs:
-                    ops.sumsq(g[a:b], self._ss)
+                    ops.sumsq(g[a:b], self._ss, self._ss_scratch)
             ops.clip_scale(self._ss, float(self.max_grad_norm), self._scale)
             scale = self._scale
         shadow = model._flat_shadow if dev_state is not None else model.shadow()

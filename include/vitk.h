@@ -189,8 +189,12 @@ VITK_API int vitk_adamw(float* p, float* g, float* m, float* v, void* p_bf16, in
  * *step_dev += increment (0 or 1); bias_corr_dev[0] = 1 − β1^t, bias_corr_dev[1] = 1/√(1 − β2^t). */
 VITK_API int vitk_adamw_tick(int64_t* step_dev, int increment, float beta1, float beta2, float* bias_corr_dev,
                vitk_stream_t stream);
-/* out[0] += Σ x²  (global gradient norm, trainer.py:2489-2493). */
-VITK_API int vitk_sumsq_f32(const float* x, int64_t n, float* out, vitk_stream_t stream);
+/* out[0] += Σ x²  (global gradient norm, trainer.py:2489-2493), summed in a fixed order: replicas holding identical
+ * gradients get bit-identical norms (torch.nn.utils.clip_grad_norm_ is deterministic too).  scratch: device buffer of
+ * vitk_sumsq_scratch_floats() floats, zero-initialised once by the caller (the kernel leaves its ticket word at zero);
+ * calls sharing a scratch buffer must be stream-ordered. */
+VITK_API int64_t vitk_sumsq_scratch_floats(void);
+VITK_API int vitk_sumsq_f32(const float* x, int64_t n, float* out, float* scratch, vitk_stream_t stream);
 /* scale[0] = min(1, max_norm / (sqrt(sumsq[0]) + 1e-6))  (torch.nn.utils.clip_grad_norm_). */
 VITK_API int vitk_clip_scale(const float* sumsq, float max_norm, float* scale, vitk_stream_t stream);
 

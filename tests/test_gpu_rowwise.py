@@ -131,3 +131,31 @@ def test_cast_and_adamw(ops):
     assert torch.allclose(ss, (grad.double() ** 2).sum().float(), rtol=1e-5)
     ops.clip_scale(ss, 1.0, sc)
     assert torch.allclose(sc, 1.0 / (grad.norm() + 1e-6), rtol=1e-5)
+
+
+def test_sumsq_is_bit_reproducible_and_accumulates(ops):
+    """Fixed summation order: replicas with identical gradients must get identical clip coefficients."""
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(86_101_264 // 8 * 8, generator=g).to(dev)            # the size of ViT-B's flat gradient buffer
+    outs = []
+    for _ in range(6):
+        ss = torch.zeros(1, device=dev)
+        ops.sumsq(x, ss)
+        outs.append(ss.item())
+    assert len(set(outs)) == 1, outs
+    assert abs(outs[0] / (x.double() ** 2).sum().item() - 1) < 1e-5
+    ss = torch.zeros(1, device=dev)
+    ops.sumsq(x[:1024], ss)
+    ops.sumsq(x[1024:4096], ss)
+    assert torch.allclose(ss, (x[:4096].double() ** 2).sum().float(), rtol=1e-5)
+
+
+def test_adamw_tick_device_step_counter(ops):
+    step = torch.zeros(1, dtype=torch.int64, device=dev)
+    bc = torch.zeros(2, device=dev)
+    for t in range(1, 4):
+        ops.adamw_tick(step, True, 0.9, 0.999, bc)
+        assert step.item() == t
+        assert torch.allclose(bc.cpu(), torch.tensor([1 - 0.9 ** t, (1 - 0.999 ** t) ** -0.5]), rtol=1e-5)
+    ops.adamw_tick(step, False, 0.9, 0.999, bc)
+    assert step.item() == 3
