@@ -318,7 +318,7 @@ def run_ours(args):
     import torch.distributed as dist
     import chest_x_ray_vit_b200 as pkg
     from chest_x_ray_vit_b200.data import DeviceFeeder
-    from chest_x_ray_vit_b200.parallel import GradSync, broadcast_parameters
+    from chest_x_ray_vit_b200.parallel import GradSync, PeerGradSync, broadcast_parameters
     from oracle import vit_oracle as O      # only for the seeded synthetic-input recipe and the cpu_baseline leg
 
     conf = CONFIGS[args.config]
@@ -342,7 +342,7 @@ def run_ours(args):
     train_gf = conf["train_gf"]
     if world > 1:
         broadcast_parameters(model)
-        GradSync.attach(model, layers_per_bucket=args.layers_per_bucket)
+        (PeerGradSync if args.sync == "peer" else GradSync).attach(model, layers_per_bucket=args.layers_per_bucket)
     opt = pkg.VitkAdamW(model, lr=2e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, max_grad_norm=1.0)
 
     g = torch.Generator().manual_seed(1 + rank)
@@ -487,7 +487,9 @@ def run_ours(args):
                            "per_gpu_batch": B, "global_batch": B * world, "tokens": cfg.seq_len, "parallelism": f"dp{world}",
                            "l2": "per-step working set (GBs of saved activations + params/grads/moments) exceeds the 126 MB L2; "
                                  "4 rotating input batches", "train_gflop_per_image": train_gf,
-                           "cuda_graph": bool(args.graph)},
+                           "cuda_graph": bool(args.graph),
+                           "grad_sync": (None if world == 1 else ("PeerGradSync: symmetric memory + copy engines over NVLink"
+                                                                  if args.sync == "peer" else "GradSync: bucketed NCCL all-reduce"))},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "loss": last_loss}
         if sustained is not None:
             line["sustained"] = sustained
@@ -573,6 +575,8 @@ def main():
                     help="after the K timed steps, keep stepping for this long and report it as `sustained` (0 = skip)")
     ap.add_argument("--graph", action="store_true", help="replay the step from a captured CUDA graph (chest_x_ray_vit_b200.graph)")
     ap.add_argument("--layers-per-bucket", type=lambda v: [int(x) for x in v.split(",")], default=[3, 3, 3, 2, 1], help="encoder layers per all-reduce bucket, in the order layers finish backward; last entry repeats (3 layers = 85 MB; tapered so the all-reduce left after backward is short)")
+    ap.add_argument("--sync", default="peer", choices=["peer", "nccl"],
+                    help="gradient all-reduce at N>1: copy engines over NVLink peer memory (PeerGradSync) or NCCL (GradSync)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

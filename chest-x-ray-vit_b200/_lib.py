@@ -63,6 +63,7 @@ _PROTOS = {
     "vitk_adamw_tick": (C.c_int, [_p, C.c_int, _f, _f, _p, _p]),
     "vitk_sumsq_f32": (C.c_int, [_p, _i64, _p, _p, _p]),
     "vitk_sumsq_scratch_floats": (C.c_int64, []),
+    "vitk_shard_mean": (C.c_int, [_p, _p, _i64, _i64, C.c_int, _f, C.c_int, _p]),
     "vitk_clip_scale": (C.c_int, [_p, _f, _p, _p]),
     "vitk_launch_count": (C.c_int64, []),
     "vitk_gemm_plan": (C.c_int, [C.POINTER(GemmArgs), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),

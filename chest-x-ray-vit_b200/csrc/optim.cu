@@ -87,6 +87,24 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float4* __restrict__ x
   }
 }
 
+// Owner's step of the peer-memory gradient all-reduce (parallel.PeerGradSync): this rank's shard of a bucket becomes the
+// mean over all ranks — own[i] = (own[i] + Σ_p peer[p][i]) / world — where peer[p] are the copies of the same shard
+// pulled from the other GPUs over NVLink by the copy engines.  Fixed summation order (own, then peers in rank order):
+// every rank later copies these very bits, so replicas stay identical.  HBM-bound: (world + 1)·4 B per element.
+__global__ void __launch_bounds__(256)
+shard_mean_kernel(float4* __restrict__ own, const float4* __restrict__ peers, long long n4, long long stride4, int n_peers,
+                  float inv_world) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float4 a = own[i];
+    for (int p = 0; p < n_peers; ++p) {
+      const float4 b = __ldg(peers + p * stride4 + i);
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    own[i] = make_float4(a.x * inv_world, a.y * inv_world, a.z * inv_world, a.w * inv_world);
+  }
+}
+
 // Device-side step counter for graph replay: t += inc; bc = {1 − β1^t, 1/sqrt(1 − β2^t)} (double pow, once per step).
 __global__ void adamw_tick_kernel(long long* step, int inc, float b1, float b2, float* bc) {
   const long long t = *step + inc;
@@ -133,6 +151,21 @@ extern "C" VITK_API int vitk_adamw_tick(int64_t* step_dev, int increment, float 
   adamw_tick_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<long long*>(step_dev), increment ? 1 : 0,
                                                                    beta1, beta2, bias_corr_dev);
   VITK_LAUNCH_CHECK("adamw_tick_kernel");
+  return 0;
+}
+
+extern "C" VITK_API int vitk_shard_mean(float* own, const float* peers, int64_t n, int64_t peer_stride, int n_peers,
+                                        float inv_world, int max_ctas, vitk_stream_t stream) {
+  VITK_REQUIRE(own && n > 0 && n % 4 == 0 && aligned16(own) && n_peers >= 0 && (n_peers == 0 || (peers && aligned16(peers))) &&
+                   peer_stride % 4 == 0 && peer_stride >= (n_peers > 0 ? n : 0),
+               VITK_EINVAL, "shard_mean: n and peer_stride must be multiples of 4, buffers 16-byte aligned");
+  const long long n4 = n / 4;
+  long long blocks = (n4 + 255) / 256;
+  const long long cap = max_ctas > 0 ? max_ctas : static_cast<long long>(num_sms()) * 2;
+  if (blocks > cap) blocks = cap;
+  shard_mean_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<float4*>(own), reinterpret_cast<const float4*>(peers), n4, peer_stride / 4, n_peers, inv_world);
+  VITK_LAUNCH_CHECK("shard_mean_kernel");
   return 0;
 }
 

@@ -290,6 +290,18 @@ class ViTForImageClassification(nn.Module):
             self._grads_clean = True
         return self._flat_grads
 
+    def set_flat_grads(self, buf: torch.Tensor) -> None:
+        """Adopt ``buf`` (fp32, ``layout.total`` elements, on the model's device) as the flat gradient buffer — e.g. a
+        symmetric-memory allocation other GPUs can read (parallel.PeerGradSync).  Launch plans are rebuilt."""
+        if buf.dtype != f32 or buf.numel() != self.layout.total or buf.device != self._flat_params.device or not buf.is_contiguous():
+            raise ValueError("set_flat_grads: need a contiguous fp32 tensor of layout.total elements on the model's device")
+        buf.zero_()
+        for p in self.param_list():
+            p.grad = None
+        self._flat_grads = buf
+        self._grads_clean = True
+        self._engine = None
+
     def stage_grads(self) -> torch.Tensor:
         """Second flat gradient buffer: a backward that finds ``param.grad`` already populated (gradient
         accumulation) writes here and autograd adds it onto ``param.grad``."""

@@ -245,5 +245,11 @@ def sumsq(x: torch.Tensor, out: torch.Tensor, scratch: Optional[torch.Tensor] = 
     _lib.check(_lib.lib().vitk_sumsq_f32(x.data_ptr(), x.numel(), out.data_ptr(), scratch.data_ptr(), _stream()), "sumsq_f32")
 
 
+def shard_mean(own: torch.Tensor, peers: Optional[torch.Tensor], peer_stride: int, n_peers: int, inv_world: float, max_ctas: int = 0):
+    """own[i] = (own[i] + Σ_p peers[p·peer_stride + i]) · inv_world  (owner's step of the peer-memory gradient all-reduce)."""
+    _lib.check(_lib.lib().vitk_shard_mean(own.data_ptr(), _ptr(peers), own.numel(), peer_stride, n_peers, inv_world, max_ctas,
+                                           _stream()), "shard_mean")
+
+
 def clip_scale(sumsq_t: torch.Tensor, max_norm: float, scale: torch.Tensor):
     _lib.check(_lib.lib().vitk_clip_scale(sumsq_t.data_ptr(), max_norm, scale.data_ptr(), _stream()), "clip_scale")

@@ -195,6 +195,12 @@ VITK_API int vitk_adamw_tick(int64_t* step_dev, int increment, float beta1, floa
  * calls sharing a scratch buffer must be stream-ordered. */
 VITK_API int64_t vitk_sumsq_scratch_floats(void);
 VITK_API int vitk_sumsq_f32(const float* x, int64_t n, float* out, float* scratch, vitk_stream_t stream);
+/* Data-parallel gradient mean, owner's step (replaces the XLA-implicit cross-replica gradient reduction of
+ * /root/reference/ViT-Training.py:106,170; used by parallel.PeerGradSync after the copy engines pulled this rank's shard
+ * of a bucket from every peer over NVLink): own[i] = (own[i] + Σ_{p<n_peers} peers[p·peer_stride + i]) · inv_world,
+ * fixed summation order.  n, peer_stride multiples of 4; max_ctas caps the grid (0 = 2 per SM). */
+VITK_API int vitk_shard_mean(float* own, const float* peers, int64_t n, int64_t peer_stride, int n_peers, float inv_world,
+               int max_ctas, vitk_stream_t stream);
 /* scale[0] = min(1, max_norm / (sqrt(sumsq[0]) + 1e-6))  (torch.nn.utils.clip_grad_norm_). */
 VITK_API int vitk_clip_scale(const float* sumsq, float max_norm, float* scale, vitk_stream_t stream);
 

@@ -20,7 +20,7 @@ WORKER = r'''
 import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, os.environ["VITK_ROOT"])
 import chest_x_ray_vit_b200 as pkg
-from chest_x_ray_vit_b200.parallel import GradSync, broadcast_parameters
+from chest_x_ray_vit_b200.parallel import GradSync, PeerGradSync, broadcast_parameters
 from oracle import vit_oracle as O
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 torch.cuda.set_device(rank)
@@ -38,7 +38,8 @@ x8, y = O.synth_inputs(cfg, per * world, g)
 lo, hi = pkg.parallel.shard_batch(per * world, rank, world)
 xs, ys = x8[lo:hi, 0].cuda(), y[lo:hi].cuda()
 m = new_model(rank)                                  # every rank starts from its own parameters
-gs = GradSync.attach(m, layers_per_bucket=(3, 3, 3, 2, 1))
+Sync = PeerGradSync if os.environ["VITK_SYNC"] == "peer" else GradSync
+gs = Sync.attach(m, layers_per_bucket=(3, 3, 3, 2, 1))
 with torch.no_grad():
     m(pixel_values=xs)                               # the bf16 shadow of the rank-local weights now exists
 broadcast_parameters(m)                              # ... and must be refreshed from rank 0's masters
@@ -73,7 +74,9 @@ sys.exit(0 if (same and ok_grad) else 1)
 '''
 
 
-def test_multi_gpu_data_parallel_steps(tmp_path):
+@pytest.mark.parametrize("sync", ["nccl", "peer"])
+def test_multi_gpu_data_parallel_steps(tmp_path, sync):
+    """sync = nccl: bucketed NCCL all-reduce (GradSync); peer: copy-engine all-reduce over NVLink peer memory (PeerGradSync)."""
     n = torch.cuda.device_count()
     if n < 2:
         pytest.skip("needs at least 2 GPUs")
@@ -82,7 +85,7 @@ def test_multi_gpu_data_parallel_steps(tmp_path):
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
-    env = dict(os.environ, VITK_ROOT=ROOT)
+    env = dict(os.environ, VITK_ROOT=ROOT, VITK_SYNC=sync)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr",
                         "127.0.0.1", "--master-port", str(port), str(script)], env=env, capture_output=True, text=True, timeout=900)
     print(r.stdout[-2000:])

@@ -5,5 +5,6 @@ N=${1:-2}
 nvidia-smi -L > gpurun_out/gpus.txt
 timeout 900 python -m pytest tests/test_gpu_multi.py -q -m gpu -x -s > gpurun_out/test_gpu_multi_n$N.log 2>&1; echo "multi test rc=$?"; grep -E "RESULT|passed|failed" gpurun_out/test_gpu_multi_n$N.log | tail -3
 python bench.py --gpus 1 --steps 20 --warmup 5 --no-cpu-baseline --sustained-seconds 0 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "n1 rc=$?"; cut -c1-200 gpurun_out/bench_n1.json
-NCCL_DEBUG=INFO NCCL_DEBUG_SUBSYS=INIT,COLL,TUNING timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 20 --warmup 5 --sustained-seconds 0 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err; echo "n$N rc=$?"; grep -vE "NCCL INFO" gpurun_out/bench_n$N.err | tail -3; cut -c1-200 gpurun_out/bench_n$N.json
-grep -E "NCCL INFO.*(Using|NVLS|Channel|algo|Algo|proto|nChannels|comm 0x.* rank 0 .*Init COMPLETE|AllReduce)" gpurun_out/bench_n$N.err | grep -E " 0 \[|rank 0|AllReduce" | head -30 > gpurun_out/nccl_info_n$N.txt; tail -12 gpurun_out/nccl_info_n$N.txt
+for SYNC in peer nccl; do
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 20 --warmup 5 --sustained-seconds 0 --sync $SYNC > gpurun_out/bench_n${N}_$SYNC.json 2> gpurun_out/bench_n${N}_$SYNC.err; echo "n$N $SYNC rc=$?"; grep -vE "NCCL INFO|OMP_NUM|\*\*\*" gpurun_out/bench_n${N}_$SYNC.err | tail -5; cut -c1-200 gpurun_out/bench_n${N}_$SYNC.json
+done

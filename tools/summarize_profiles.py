@@ -61,21 +61,30 @@ with open(os.path.join(P, f"{tag}_ncu_full_summary.csv"), "w") as out:
                 else:
                     vals.append("")
             w.writerow([rep, row[hdr.index("ID")], name] + vals)
-# ---- DRAM traffic of the dominant kernel (all tcgen05 GEMM launches), per launch, for bench.py's roofline.traffic
+# ---- DRAM traffic of the dominant kernel (tcgen05 GEMM launches), per launch and per shape, for bench.py's roofline.traffic.
+# Shape = (grid, template instantiation): the M = 16 CLS-row launches of the top layer (small grids) are listed but excluded
+# from the headline average, which covers the dense launches of one middle layer (forward + backward).
 import json
 rows = list(csv.DictReader(open(os.path.join(P, f"{tag}_ncu_full_summary.csv"))))
-tot_b, n = 0.0, 0
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+per, tot_b, n = [], 0.0, 0
 for r in rows:
     if "gemm" not in r["kernel"]:
         continue
+    b = 0.0
     for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
         v, u = r[k].split()
-        tot_b += float(v) * UNIT[u]
-    n += 1
+        b += float(v) * UNIT[u]
+    grid = r["launch__grid_size"].split()[0]
+    dense = float(grid) >= 100
+    per.append({"report": r["report"], "id": r["id"], "kernel": r["kernel"], "grid": grid, "dram_bytes": b, "duration": r["gpu__time_duration.sum"],
+                "tensor_pipe_pct": r["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"].split()[0], "dense": dense})
+    if dense:
+        tot_b += b
+        n += 1
 if n:
-    json.dump({"kernel": "gemm2_bf16_kernel / gemm_bf16_kernel", "launches_profiled": n, "dram_bytes_per_launch": tot_b / n,
-               "source": f"profiles/{tag}_ncu_full_summary.csv (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, "
-                         "one layer's forward + backward GEMMs inside a training step)"},
+    json.dump({"kernel": "gemm2_bf16_kernel", "launches_profiled": n, "dram_bytes_per_launch": tot_b / n, "per_shape": per,
+               "source": f"profiles/{tag}_ncu_full_summary.csv (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum; the 12 "
+                         "dense GEMM launches of one middle encoder layer, forward + backward, inside a training step)"},
               open(os.path.join(P, f"{tag}_roofline_traffic.json"), "w"), indent=1)
 print("wrote", [x for x in os.listdir(P) if x.startswith(tag)])
