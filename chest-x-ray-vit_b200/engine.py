@@ -34,33 +34,73 @@ _PLAN_GRAPHS = os.environ.get("VITK_PLAN_GRAPHS", "1") != "0"
 class _Plan:
     """A list of (cfunc, args) launches; ``run`` appends the stream and checks return codes."""
 
+    tail_stream: Optional[torch.cuda.Stream] = None    # set per plan by the arena: stream for ragged-M tail GEMMs
+    pairs = 74                                         # CTA pairs of the device (SMs / 2), set by the engine
+
     def __init__(self):
         self.steps: List[Tuple[object, tuple, str]] = []
         self.gemm_flops: Dict[int, float] = {}      # step index → 2·M·N·K (bench.py's roofline leg)
-        self.side_steps = set()                     # indices of steps launched on the side stream
+        self.step_stream: Dict[int, int] = {}       # step index → 1 (side stream: weight gradients) | 2 (tail stream)
         self._segments = {}                         # (callbacks?, side stream?) → [(CUDAGraph | None, callback | None)]
         self._warm = set()
         self._keep = []      # keeps GemmArgs structs alive
-        self._side = False
+        self._side = 0
+        self.split_ragged = True
 
     def side(self, on: bool):
         """Steps added while on=True are launched on the engine's side stream (weight-gradient work that only the
         optimizer consumes); fork()/join() order it against the main chain."""
-        self._side = on
+        self._side = 1 if on else 0
 
-    def fork(self):
-        self.steps.append((None, (), "fork"))        # side stream waits for everything enqueued on main so far
+    def fork(self, which: int = 1):
+        self.steps.append((None, (which,), "fork"))  # stream `which` waits for everything enqueued on main so far
 
-    def join(self):
-        self.steps.append((None, (), "join"))        # main stream waits for everything enqueued on side so far
+    def join(self, which: int = 1):
+        self.steps.append((None, (which,), "join"))  # main stream waits for everything enqueued on stream `which` so far
 
     def add(self, name: str, *args):
         if self._side:
-            self.side_steps.add(len(self.steps))
+            self.step_stream[len(self.steps)] = self._side
         self.steps.append((getattr(_lib.lib(), name), args, name))
+
+    def _rounds(self, M, N, K, epilogue, a_mn, b_mn, split_k, tile_n, max_ctas) -> int:
+        try:
+            items = ops.gemm_plan(M, N, K, epilogue=epilogue, a_mn_major=a_mn, b_mn_major=b_mn, split_k=split_k, tile_n=tile_n,
+                                  max_ctas=max_ctas, sms=2 * self.pairs)["work_items"]
+        except RuntimeError:
+            return 0
+        pairs = min(self.pairs, max_ctas // 2) if max_ctas else self.pairs
+        return -(-items // pairs)
 
     def gemm(self, a, b, M, N, K, d, epilogue, a_mn=False, b_mn=False, d2=None, bias=None, aux=None, rows_in=0,
              rows_out=0, row_off=0, ldd=None, ld_aux=None, split_k=0, tile_n=0, variant=0, max_ctas=0):
+        """One GEMM launch — or two when M is ragged: the CTA-pair kernel works on 256-row bands, so a few rows past a
+        multiple of 256 (ViT-L at batch 8: M = 4616 = 18·256 + 8) cost every N-tile of a whole extra band, i.e. often
+        a whole extra round of the persistent schedule (N = 1024: 76 tiles on 74 pairs).  When cutting the tail off
+        saves a round, the bands go to the pair kernel and the ≤ 64 tail rows to the single-CTA kernel on the tail
+        stream, concurrently, on the SMs the pair grid leaves idle."""
+        tail = M % 256
+        if (self.split_ragged and not a_mn and epilogue != EPI_PATCH_F32 and variant == 0 and rows_in == 0 and 0 < tail <= 64
+                and M > 1024 and N % 128 == 0):
+            main = M - tail
+            r_all = self._rounds(M, N, K, epilogue, a_mn, b_mn, split_k, tile_n, max_ctas)
+            r_main = self._rounds(main, N, K, epilogue, a_mn, b_mn, split_k, tile_n, max_ctas)
+            if 0 < r_main < r_all:
+                side = self._side
+                self.fork(2)
+                self._side = 2
+                self._gemm_one(a[main:], b, tail, N, K, d[main:], epilogue, a_mn, b_mn, None if d2 is None else d2[main:], bias,
+                               None if aux is None else aux[main:], 0, 0, 0, ldd, ld_aux, 0, 0, 1, 0)
+                self._side = side
+                self._gemm_one(a, b, main, N, K, d, epilogue, a_mn, b_mn, d2, bias, aux, 0, 0, 0, ldd, ld_aux, split_k, tile_n,
+                               variant, max_ctas)
+                self.join(2)
+                return
+        self._gemm_one(a, b, M, N, K, d, epilogue, a_mn, b_mn, d2, bias, aux, rows_in, rows_out, row_off, ldd, ld_aux, split_k,
+                       tile_n, variant, max_ctas)
+
+    def _gemm_one(self, a, b, M, N, K, d, epilogue, a_mn, b_mn, d2, bias, aux, rows_in, rows_out, row_off, ldd, ld_aux, split_k,
+                  tile_n, variant, max_ctas):
         g = GemmArgs()
         g.a, g.b, g.M, g.N, g.K = a.data_ptr(), b.data_ptr(), M, N, K
         g.lda, g.ldb = a.stride(0), b.stride(0)
@@ -74,31 +114,34 @@ class _Plan:
         self._keep.append(g)
         self.gemm_flops[len(self.steps)] = 2.0 * M * N * K
         if self._side:
-            self.side_steps.add(len(self.steps))
+            self.step_stream[len(self.steps)] = self._side
         self.steps.append((_lib.lib().vitk_gemm_bf16, (C.byref(g),), "vitk_gemm_bf16"))
 
     def call(self, fn: Callable[[], None]):
         self.steps.append((None, (fn,), "python"))
 
     def _run_range(self, lo: int, hi: int, stream: int, side_stream: Optional[torch.cuda.Stream], run_py: bool = True):
-        side = side_stream.cuda_stream if side_stream is not None else stream
+        streams = {1: side_stream, 2: self.tail_stream}
+        handles = {k: (v.cuda_stream if v is not None else stream) for k, v in streams.items()}
         for i in range(lo, hi):
             fn, args, name = self.steps[i]
             if fn is None:
                 if name == "python":
                     if run_py:
                         args[0]()
-                elif side_stream is not None:
+                elif streams[args[0]] is not None:
+                    other = streams[args[0]]
                     main = torch.cuda.current_stream()
                     ev = torch.cuda.Event()
                     if name == "fork":
                         ev.record(main)
-                        side_stream.wait_event(ev)
+                        other.wait_event(ev)
                     else:
-                        ev.record(side_stream)
+                        ev.record(other)
                         main.wait_event(ev)
                 continue
-            rc = fn(*args, side if i in self.side_steps else stream)
+            which = self.step_stream.get(i, 0)
+            rc = fn(*args, handles[which] if which else stream)
             if rc != 0:
                 _lib.check(rc, name)
 
@@ -112,7 +155,7 @@ class _Plan:
         if not _PLAN_GRAPHS or torch.cuda.is_current_stream_capturing():
             self._run_range(0, len(self.steps), stream, side_stream, callbacks)
             return
-        key = (callbacks, side_stream is not None)
+        key = (callbacks, side_stream is not None, self.tail_stream is not None)
         segs = self._segments.get(key)
         if segs is None:
             if key not in self._warm:
@@ -221,6 +264,8 @@ class Arena:
         eps = cfg.layer_norm_eps
         scale = 64 ** -0.5
         pl = _Plan()
+        pl.tail_stream = eng.tail_stream
+        pl.split_ragged = os.environ.get("VITK_SPLIT_RAGGED", "1") != "0"
         h0 = self.h[0]
         pl.add("vitk_embed_cls", _p(w["cls"]), _p(w["pos"]), B, T, D, _p(h0))
         pl.gemm(self.apatch, w["wp16"], B * P, D, 768, h0, EPI_PATCH_F32, bias=w["bp"], aux=w["pos"], rows_in=P, rows_out=T,
@@ -257,6 +302,17 @@ class Arena:
         T, P, B, M = cfg.seq_len, cfg.num_patches, self.B, self.M
         scale = 64 ** -0.5
         pl = _Plan()
+        pl.tail_stream = eng.tail_stream
+        pl.split_ragged = os.environ.get("VITK_SPLIT_RAGGED", "1") != "0"
+        # host callbacks (= breaks between CUDA-graph segments) only where the gradient sync completes a bucket
+        ends = eng.grad_sync.bucket_end_layers() if eng.grad_sync is not None else set()
+        done_hi = [L - 1]
+
+        def layer_done(l):
+            if l in ends:
+                lo, hi = l, done_hi[0]
+                done_hi[0] = l - 1
+                pl.call(lambda lo=lo, hi=hi: eng._layers_grads_ready(lo, hi))
         mc = eng.comm_reserved_ctas()         # GEMMs of the backward leave SMs to the overlapped all-reduce
         _gemm = pl.gemm
 
@@ -299,7 +355,7 @@ class Arena:
         pl.gemm(self.dqkv, lw["wqkv16"], M, D, 3 * D, self.dn, EPI_STORE_BF16, b_mn=True)
         pl.add("vitk_layernorm_bwd", _p(self.dn), _p(self.h[l]), D, _p(st[0]), _p(st[1]), _p(lw["g1"]), _p(dh1), M, D,
                _p(dh), _p(lg["g1"]), _p(lg["b1"]), _p(g["layers"][l - 1]["bf2"]) if l > 0 else None)
-        pl.call(lambda l=l: eng._layer_grads_ready(l))
+        layer_done(l)
         # ---- layers L-2 … 0: dense
         # Dense layers.  Weight gradients (and the two wide bias column sums) are consumed only by the optimizer, so
         # they go to a side stream: fork after the tensor they read is produced, join once per layer before the
@@ -338,10 +394,11 @@ class Arena:
             pl.join()          # side work of this layer read dh / du / dh1 / dqkv, which the next kernels overwrite
             pl.add("vitk_layernorm_bwd", _p(self.dn), _p(self.h[l]), D, _p(st[0]), _p(st[1]), _p(lw["g1"]), _p(dh1), M, D,
                    _p(dh), _p(lg["g1"]), _p(lg["b1"]), _p(g["layers"][l - 1]["bf2"]) if l > 0 else None)
-            pl.call(lambda l=l: eng._layer_grads_ready(l))
+            layer_done(l)
         pl.add("vitk_embed_bwd", _p(dh), B, T, D, _p(g["pos"]), _p(g["cls"]), _p(g["bp"]), _p(self.dpatch))
         pl.gemm(self.dpatch, self.apatch, D, 768, B * P, g["wp"], EPI_ACCUM_F32, a_mn=True, b_mn=True)
-        pl.call(lambda: eng._rest_grads_ready())
+        if eng.grad_sync is not None:
+            pl.call(lambda: eng._rest_grads_ready())
         return pl
 
 
@@ -354,6 +411,8 @@ class Engine:
         self.arenas: Dict[Tuple[int, bool], Arena] = {}
         self.grad_sync = None            # parallel.GradSync, set by the caller for N>1
         self.side_stream = torch.cuda.Stream(device=self.dev) if os.environ.get("VITK_SIDE_STREAM", "1") != "0" else None
+        self.tail_stream = torch.cuda.Stream(device=self.dev) if os.environ.get("VITK_SIDE_STREAM", "1") != "0" else None
+        _Plan.pairs = torch.cuda.get_device_properties(self.dev).multi_processor_count // 2
         self.w = self._weight_views(model.flat_parameters(), model.shadow())
         self.g = self._weight_views(model.flat_grads(), None)
         self._g_stage = None
@@ -503,9 +562,9 @@ class Engine:
         return tuple((chunks[i].view(sh) if chunks[i].numel() == k else chunks[i][:k].view(sh)) if nd else None
                      for (i, k, sh), nd in zip(self._spans, needs))
 
-    def _layer_grads_ready(self, l: int) -> None:
+    def _layers_grads_ready(self, lo: int, hi: int) -> None:
         if self.grad_sync is not None:
-            self.grad_sync.layer_ready(l)
+            self.grad_sync.layers_ready(lo, hi)
 
     def _rest_grads_ready(self) -> None:
         if self.grad_sync is not None:

@@ -63,6 +63,22 @@ class GradSync:
             self.pending = []
             self.bucket_index += 1
 
+    def bucket_end_layers(self) -> set:
+        """Layers whose ``layer_ready`` call completes a bucket (layers finish in descending order).  The engine only
+        needs a host callback — i.e. a break in its CUDA-graph segments — at these; the others are replayed for free."""
+        ends, pending, bi = set(), 0, 0
+        for l in reversed(range(len(self.layer_ranges))):
+            pending += 1
+            if pending >= self.bucket_sizes[min(bi, len(self.bucket_sizes) - 1)] or l == 0:
+                ends.add(l)
+                pending, bi = 0, bi + 1
+        return ends
+
+    def layers_ready(self, lo: int, hi: int) -> None:
+        """Layers lo … hi (inclusive; a whole bucket) have their weight gradients enqueued on the current stream."""
+        for l in range(hi, lo - 1, -1):
+            self.layer_ready(l)
+
     def rest_ready(self) -> None:
         for s, e in self.rest_ranges:
             self._reduce(s, e)

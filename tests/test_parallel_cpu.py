@@ -99,6 +99,19 @@ def test_gradsync_world2_gloo():
         assert all(oks), (rank, oks)
 
 
+def test_bucket_end_layers_follow_the_taper():
+    lay = pkg.modeling.FlatLayout(pkg.ViTConfig(**dict(TINY, num_hidden_layers=12)))
+    gs = GradSync(lay.layer_range, lay.rest_ranges, layers_per_bucket=(3, 3, 3, 2, 1))
+    assert gs.bucket_end_layers() == {9, 6, 3, 1, 0}            # buckets {11,10,9} {8,7,6} {5,4,3} {2,1} {0}
+    assert GradSync(lay.layer_range, lay.rest_ranges, layers_per_bucket=5).bucket_end_layers() == {7, 2, 0}
+    # layers_ready(lo, hi) reduces exactly the bucket's contiguous range (world size 1: counted, not communicated)
+    seen = []
+    gs._reduce = lambda s, e: seen.append((s, e))
+    gs.begin(torch.zeros(lay.total))
+    gs.layers_ready(9, 11)
+    assert seen == [(lay.layer_range[9][0], lay.layer_range[11][1])]
+
+
 def test_shard_batch():
     assert shard_batch(128, 3, 8) == (48, 64)
     with pytest.raises(ValueError):
