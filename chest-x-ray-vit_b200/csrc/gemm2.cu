@@ -701,7 +701,8 @@ static int dispatch_major2(const vitk_gemm_args& a, const Gemm2Params& p, int pa
 static double kblock_cycles(int bn) { return bn == 256 ? 500.0 : (bn == 192 ? VITK_K192 : 390.0); }
 constexpr double kTileFixedCycles = 1500.0;   // accumulator hand-over + pipeline refill per tile
 
-static void choose_tiling2(const vitk_gemm_args& a, int pairs, int* bn_out, int* splits_out, int* n_half_out) {
+static void choose_tiling2(const vitk_gemm_args& a, int pairs, int* bn_out, int* splits_out, int* n_half_out,
+                           double* cost_out = nullptr) {
   const long long mt = (a.M + 2 * k2BM - 1) / (2 * k2BM);
   const long long kb_total = (a.K + k2BK - 1) / k2BK;
   double best = 1e30;
@@ -746,6 +747,24 @@ static void choose_tiling2(const vitk_gemm_args& a, int pairs, int* bn_out, int*
       }
     }
   }
+  if (cost_out) *cost_out = best;
+}
+
+// Data-gradient GEMMs (K-major A, MN-major B, plain bf16 store) whose M is ragged against the pair kernel's 256-row bands
+// can quantise badly on 74 pairs yet perfectly on 148 single CTAs with 128-row bands — ViT-L at batch 8: M = 4616 → 19
+// bands × 4 tiles of 256 columns = 76 tiles (two pairs get a second tile) against 37 × 4 = 148 tiles = exactly one wave.
+// Measured there (tools/bench_gemm.py, VITK_BG_M=4616 VITK_BG_D=1024 VITK_BG_F=4096): fc1 dgrad 43.2 → 35.7 µs,
+// qkv dgrad 35.8 → 28.8 µs, out dgrad 19.5 → 16.5 µs.  Per K block a single CTA (which stages the whole B tile itself)
+// costs ≈ 1.1 × the pair kernel's 256-wide block for this operand layout.
+static bool single_cta_wins(const vitk_gemm_args& a, double pair_cost, int sms) {
+  if (a.variant != 0 || a.tile_n != 0 || a.max_ctas != 0 || a.a_mn_major || !a.b_mn_major || a.epilogue != VITK_EPI_STORE_BF16 ||
+      a.N % 256 != 0)
+    return false;
+  const long long tiles = ((a.M + 127) / 128) * (a.N / 256);
+  const long long waves = (tiles + sms - 1) / sms;
+  const long long kb = (a.K + k2BK - 1) / k2BK;
+  const double cost = static_cast<double>(waves) * (kb * 1.1 * kblock_cycles(256) + kTileFixedCycles);
+  return cost < 0.9 * pair_cost;
 }
 
 // Called by vitk_gemm_bf16 (gemm.cu) after argument validation.  Returns VITK_EINVAL-free 1 when the
@@ -767,11 +786,13 @@ int gemm2_try_launch(const vitk_gemm_args& a, cudaStream_t stream, bool* handled
   // max_ctas leaves SMs free for a concurrent NCCL all-reduce (tile choice then balances waves over fewer pairs)
   const int pairs_avail = (a.max_ctas > 0 && a.max_ctas < sms ? a.max_ctas : sms) / 2;
   int bn = 0, splits = 1, n_half = 0;
-  choose_tiling2(a, pairs_avail, &bn, &splits, &n_half);
+  double pair_cost = 0;
+  choose_tiling2(a, pairs_avail, &bn, &splits, &n_half, &pair_cost);
   if (bn == 0) {
     VITK_REQUIRE(a.variant != 2, VITK_EINVAL, "gemm: no CTA-pair tiling for N=%lld tile_n=%d", (long long)a.N, a.tile_n);
     return 0;
   }
+  if (single_cta_wins(a, pair_cost, sms)) return 0;     // falls through to the single-CTA kernel (gemm.cu), 256-wide tiles
   Gemm2Params p;
   p.M = static_cast<int>(a.M); p.N = static_cast<int>(a.N); p.K = static_cast<int>(a.K);
   const int m_tiles = (p.M + 2 * k2BM - 1) / (2 * k2BM);

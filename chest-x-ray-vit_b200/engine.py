@@ -34,8 +34,7 @@ _PLAN_GRAPHS = os.environ.get("VITK_PLAN_GRAPHS", "1") != "0"
 class _Plan:
     """A list of (cfunc, args) launches; ``run`` appends the stream and checks return codes."""
 
-    tail_stream: Optional[torch.cuda.Stream] = None    # set per plan by the arena: stream for ragged-M tail GEMMs
-    pairs = 74                                         # CTA pairs of the device (SMs / 2), set by the engine
+    tail_stream: Optional[torch.cuda.Stream] = None    # optional second auxiliary stream (fork(2) / join(2)); unused by default
 
     def __init__(self):
         self.steps: List[Tuple[object, tuple, str]] = []
@@ -45,7 +44,6 @@ class _Plan:
         self._warm = set()
         self._keep = []      # keeps GemmArgs structs alive
         self._side = 0
-        self.split_ragged = True
 
     def side(self, on: bool):
         """Steps added while on=True are launched on the engine's side stream (weight-gradient work that only the
@@ -63,39 +61,8 @@ class _Plan:
             self.step_stream[len(self.steps)] = self._side
         self.steps.append((getattr(_lib.lib(), name), args, name))
 
-    def _rounds(self, M, N, K, epilogue, a_mn, b_mn, split_k, tile_n, max_ctas) -> int:
-        try:
-            items = ops.gemm_plan(M, N, K, epilogue=epilogue, a_mn_major=a_mn, b_mn_major=b_mn, split_k=split_k, tile_n=tile_n,
-                                  max_ctas=max_ctas, sms=2 * self.pairs)["work_items"]
-        except RuntimeError:
-            return 0
-        pairs = min(self.pairs, max_ctas // 2) if max_ctas else self.pairs
-        return -(-items // pairs)
-
     def gemm(self, a, b, M, N, K, d, epilogue, a_mn=False, b_mn=False, d2=None, bias=None, aux=None, rows_in=0,
              rows_out=0, row_off=0, ldd=None, ld_aux=None, split_k=0, tile_n=0, variant=0, max_ctas=0):
-        """One GEMM launch — or two when M is ragged: the CTA-pair kernel works on 256-row bands, so a few rows past a
-        multiple of 256 (ViT-L at batch 8: M = 4616 = 18·256 + 8) cost every N-tile of a whole extra band, i.e. often
-        a whole extra round of the persistent schedule (N = 1024: 76 tiles on 74 pairs).  When cutting the tail off
-        saves a round, the bands go to the pair kernel and the ≤ 64 tail rows to the single-CTA kernel on the tail
-        stream, concurrently, on the SMs the pair grid leaves idle."""
-        tail = M % 256
-        if (self.split_ragged and not a_mn and epilogue != EPI_PATCH_F32 and variant == 0 and rows_in == 0 and 0 < tail <= 64
-                and M > 1024 and N % 128 == 0):
-            main = M - tail
-            r_all = self._rounds(M, N, K, epilogue, a_mn, b_mn, split_k, tile_n, max_ctas)
-            r_main = self._rounds(main, N, K, epilogue, a_mn, b_mn, split_k, tile_n, max_ctas)
-            if 0 < r_main < r_all:
-                side = self._side
-                self.fork(2)
-                self._side = 2
-                self._gemm_one(a[main:], b, tail, N, K, d[main:], epilogue, a_mn, b_mn, None if d2 is None else d2[main:], bias,
-                               None if aux is None else aux[main:], 0, 0, 0, ldd, ld_aux, 0, 0, 1, 0)
-                self._side = side
-                self._gemm_one(a, b, main, N, K, d, epilogue, a_mn, b_mn, d2, bias, aux, 0, 0, 0, ldd, ld_aux, split_k, tile_n,
-                               variant, max_ctas)
-                self.join(2)
-                return
         self._gemm_one(a, b, M, N, K, d, epilogue, a_mn, b_mn, d2, bias, aux, rows_in, rows_out, row_off, ldd, ld_aux, split_k,
                        tile_n, variant, max_ctas)
 
@@ -264,8 +231,6 @@ class Arena:
         eps = cfg.layer_norm_eps
         scale = 64 ** -0.5
         pl = _Plan()
-        pl.tail_stream = eng.tail_stream
-        pl.split_ragged = os.environ.get("VITK_SPLIT_RAGGED", "1") != "0"
         h0 = self.h[0]
         pl.add("vitk_embed_cls", _p(w["cls"]), _p(w["pos"]), B, T, D, _p(h0))
         pl.gemm(self.apatch, w["wp16"], B * P, D, 768, h0, EPI_PATCH_F32, bias=w["bp"], aux=w["pos"], rows_in=P, rows_out=T,
@@ -302,8 +267,6 @@ class Arena:
         T, P, B, M = cfg.seq_len, cfg.num_patches, self.B, self.M
         scale = 64 ** -0.5
         pl = _Plan()
-        pl.tail_stream = eng.tail_stream
-        pl.split_ragged = os.environ.get("VITK_SPLIT_RAGGED", "1") != "0"
         # host callbacks (= breaks between CUDA-graph segments) only where the gradient sync completes a bucket
         ends = eng.grad_sync.bucket_end_layers() if eng.grad_sync is not None else set()
         done_hi = [L - 1]
@@ -411,8 +374,6 @@ class Engine:
         self.arenas: Dict[Tuple[int, bool], Arena] = {}
         self.grad_sync = None            # parallel.GradSync, set by the caller for N>1
         self.side_stream = torch.cuda.Stream(device=self.dev) if os.environ.get("VITK_SIDE_STREAM", "1") != "0" else None
-        self.tail_stream = torch.cuda.Stream(device=self.dev) if os.environ.get("VITK_SIDE_STREAM", "1") != "0" else None
-        _Plan.pairs = torch.cuda.get_device_properties(self.dev).multi_processor_count // 2
         self.w = self._weight_views(model.flat_parameters(), model.shadow())
         self.g = self._weight_views(model.flat_grads(), None)
         self._g_stage = None

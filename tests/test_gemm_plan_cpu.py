@@ -49,18 +49,3 @@ def test_fewer_sms_rebalance_and_errors():
     with pytest.raises(RuntimeError):
         ops.gemm_plan(M, 100, D, epilogue=ops.EPI_STORE_BF16)           # N must be a multiple of 128
 
-
-def test_ragged_m_split_decision():
-    """Engine-level split of a GEMM whose M is a few rows past a multiple of 256 (the CTA-pair kernel's band height): taken
-    where it saves a round of the persistent schedule (ViT-L at batch 8, M = 4616), not taken for the headline ViT-B batch
-    16 (M = 9232: the static schedule already divides evenly), never for weight-gradient layouts."""
-    import chest_x_ray_vit_b200 as pkg
-    from chest_x_ray_vit_b200.engine import _Plan
-    from chest_x_ray_vit_b200._lib import EPI_BIAS_RESID_F32, EPI_STORE_BF16
-    pl = _Plan()
-    pl.pairs = 74
-    r = lambda M, N, K, epi, b_mn=False: pl._rounds(M, N, K, epi, False, b_mn, 0, 0, 0)
-    assert (r(4616, 1024, 1024, EPI_BIAS_RESID_F32), r(4608, 1024, 1024, EPI_BIAS_RESID_F32)) == (2, 1)
-    assert (r(4616, 1024, 4096, EPI_STORE_BF16, True), r(4608, 1024, 4096, EPI_STORE_BF16, True)) == (2, 1)
-    assert r(9232, 768, 768, EPI_BIAS_RESID_F32) == r(9216, 768, 768, EPI_BIAS_RESID_F32)
-    assert r(9232, 3072, 768, EPI_STORE_BF16) == r(9216, 3072, 768, EPI_STORE_BF16)

@@ -13,7 +13,7 @@ import chest_x_ray_vit_b200 as pkg  # noqa: E402
 ops = pkg.ops
 dev = "cuda"
 bf16 = torch.bfloat16
-M, D, F = 9232, 768, 3072
+M, D, F = (int(os.environ.get(k, v)) for k, v in (("VITK_BG_M", 9232), ("VITK_BG_D", 768), ("VITK_BG_F", 3072)))   # ViT-L at batch 8: 4616 1024 4096
 PEAK = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["bf16_tflops"] \
     if os.path.exists(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")) else 1590.0
 
@@ -94,6 +94,8 @@ def run(c, reps=10, **kw):
 configs = [dict(variant=1), dict(variant=2), dict(variant=2, tile_n=128), dict(variant=2, tile_n=192), dict(variant=2, tile_n=256)]
 if len(sys.argv) > 1 and sys.argv[1] == "--quick":
     configs = [dict(variant=2), dict(variant=2, tile_n=256)]
+if len(sys.argv) > 1 and sys.argv[1] == "--auto":
+    configs = [dict(variant=0), dict(variant=1)]
 if len(sys.argv) > 1 and sys.argv[1] == "--cublas":
     configs = [dict(variant=2), dict(cublas=True)]
 if len(sys.argv) > 1 and sys.argv[1] == "--none":         # imported as a module (tools/gemm_timeline.py)
