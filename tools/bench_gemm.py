@@ -94,6 +94,9 @@ def run(c, reps=10, **kw):
 configs = [dict(variant=1), dict(variant=2), dict(variant=2, tile_n=128), dict(variant=2, tile_n=192), dict(variant=2, tile_n=256)]
 if len(sys.argv) > 1 and sys.argv[1] == "--quick":
     configs = [dict(variant=2), dict(variant=2, tile_n=256)]
+if len(sys.argv) > 1 and sys.argv[1] == "--splitk":        # weight-gradient launches only, split-K factor forced
+    configs = [dict(variant=2)] + [dict(variant=2, split_k=k) for k in (1, 2, 3, 4, 5, 6, 8, 10)]
+    CASES = [c for c in CASES if "wgrad" in c["name"]]
 if len(sys.argv) > 1 and sys.argv[1] == "--auto":
     configs = [dict(variant=0), dict(variant=1)]
 if len(sys.argv) > 1 and sys.argv[1] == "--cublas":
@@ -115,7 +118,8 @@ if not configs:
     CASES_TO_RUN = []
 else:
     CASES_TO_RUN = CASES
-print(f"{'gemm':14s} {'M':>5s} {'N':>5s} {'K':>5s} | " + " | ".join(f"{str(k):>24s}" for k in configs))
+compact = len(configs) > 4
+print(f"{'gemm':14s} {'M':>5s} {'N':>5s} {'K':>5s} | " + " | ".join(f"{str(k):>24s}" if not compact else f"{str(k.get('split_k', 'auto')):>7s}" for k in configs))
 tot = [0.0] * len(configs)
 for c in CASES_TO_RUN:
     fl = 2.0 * c["M"] * c["N"] * c["K"]
@@ -123,10 +127,10 @@ for c in CASES_TO_RUN:
     for i, k in enumerate(configs):
         try:
             ms = run(c, **k)
-            cells.append(f"{ms * 1e3:7.1f}us {fl / ms / 1e9:6.0f}TF {100 * fl / ms / 1e9 / PEAK:4.0f}%")
+            cells.append(f"{ms * 1e3:7.1f}us {fl / ms / 1e9:6.0f}TF {100 * fl / ms / 1e9 / PEAK:4.0f}%" if not compact else f"{ms * 1e3:7.1f}")
             tot[i] += ms
         except RuntimeError as e:
             cells.append(f"{'n/a':>24s}")
             tot[i] += float("nan")
-    print(f"{c['name']} {c['M']:5d} {c['N']:5d} {c['K']:5d} | " + " | ".join(f"{x:>24s}" for x in cells))
+    print(f"{c['name']} {c['M']:5d} {c['N']:5d} {c['K']:5d} | " + " | ".join(f"{x:>24s}" if not compact else f"{x:>7s}" for x in cells))
 print("sum over one layer's 12 GEMMs (ms):", ["%.3f" % x for x in tot])
