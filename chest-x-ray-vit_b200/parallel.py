@@ -12,6 +12,7 @@ compute stream only waits after the last bucket, right before the optimizer need
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -35,6 +36,7 @@ class GradSync:
         self.pending: List[int] = []
         self.bytes_reduced = 0
         self.collectives = 0
+        self._deferred: Optional[Tuple[int, int]] = None
 
     @classmethod
     def attach(cls, model, process_group=None, layers_per_bucket=3) -> "GradSync":
@@ -51,6 +53,7 @@ class GradSync:
         self.flat = model_or_flat if isinstance(model_or_flat, torch.Tensor) else model_or_flat.flat_grads()
         self.works, self.pending = [], []
         self.bucket_index = 0
+        self._deferred = None
 
     def layer_ready(self, l: int) -> None:
         """Layer ``l``'s weight gradients are enqueued on the current stream (layers finish in
@@ -59,7 +62,14 @@ class GradSync:
         size = self.bucket_sizes[min(self.bucket_index, len(self.bucket_sizes) - 1)]
         if len(self.pending) >= size or l == 0:
             lo, hi = min(self.pending), max(self.pending)
-            self._reduce(self.layer_ranges[lo][0], self.layer_ranges[hi][1])
+            rng = (self.layer_ranges[lo][0], self.layer_ranges[hi][1])
+            if l == 0:
+                # the bucket that ends with layer 0 finishes only a few kernels before everything else (embeddings,
+                # biases): it is reduced together with those in rest_ready — fewer, larger operations in the part of the
+                # all-reduce that no backward work is left to hide
+                self._deferred = rng
+            else:
+                self._reduce(*rng)
             self.pending = []
             self.bucket_index += 1
 
@@ -79,10 +89,25 @@ class GradSync:
         for l in range(hi, lo - 1, -1):
             self.layer_ready(l)
 
+    def _final_ranges(self) -> List[Tuple[int, int]]:
+        """The deferred last layer bucket and the non-layer ranges, adjacent ones coalesced."""
+        rs = sorted(([self._deferred] if self._deferred is not None else []) + [r for r in self.rest_ranges if r[1] > r[0]])
+        self._deferred = None
+        out: List[Tuple[int, int]] = []
+        for s, e in rs:
+            if out and out[-1][1] == s:
+                out[-1] = (out[-1][0], e)
+            else:
+                out.append((s, e))
+        return out
+
     def rest_ready(self) -> None:
-        for s, e in self.rest_ranges:
-            self._reduce(s, e)
+        self._reduce_many(self._final_ranges())
         self.wait()
+
+    def _reduce_many(self, ranges: List[Tuple[int, int]]) -> None:
+        for s, e in ranges:
+            self._reduce(s, e)
 
     def wait(self) -> None:
         for w in self.works:
@@ -144,10 +169,15 @@ class PeerGradSync(GradSync):
         per_bucket = max(self.bucket_sizes) * longest
         self.max_shard = (per_bucket + self.world - 1) // self.world // 4 * 4 + 4
         self.scratch = torch.empty((self.world - 1) * self.max_shard, dtype=torch.float32, device=dev)
-        self.comm = torch.cuda.Stream(device=dev)
+        # highest stream priority: the persistent backward GEMMs keep every SM busy (227 KB of shared memory per CTA leaves no
+        # room for a second CTA), so the small mean / barrier kernels only get SMs at kernel boundaries — and must get them
+        # FIRST there, or they starve (measured: 485 µs for a 20 µs kernel at default priority)
+        self.comm = torch.cuda.Stream(device=dev, priority=-1)
+        self.mean_ctas = int(os.environ.get("VITK_PEER_MEAN_CTAS", "0"))      # 0 = two CTAs per SM: short and wide
         self._chan = 0
         self._last = None
         self.timeout_ms = 20000           # a protocol bug traps after 20 s instead of hanging the GPUs
+        self.timing = None                # set to [] to collect (start, end, [events], t_host) per bucket (diagnostics)
 
     @classmethod
     def attach(cls, model, process_group=None, layers_per_bucket=3) -> "PeerGradSync":
@@ -175,35 +205,64 @@ class PeerGradSync(GradSync):
         return lo, min(lo + c, end)
 
     def _reduce(self, start: int, end: int) -> None:
-        if end <= start:
+        self._reduce_many([(start, end)])
+
+    def _reduce_many(self, ranges: List[Tuple[int, int]]) -> None:
+        """One barrier / pull / mean / barrier / pull round over one or several ranges of the buffer."""
+        ranges = [(s, e) for s, e in ranges if e > s]
+        if not ranges:
             return
         from . import ops
         flat = self.sym
-        self.bytes_reduced += (end - start) * 4
+        self.bytes_reduced += sum(e - s for s, e in ranges) * 4
         self.collectives += 1
-        ready = torch.cuda.Event()
+        ready = torch.cuda.Event(enable_timing=self.timing is not None)
         ready.record(torch.cuda.current_stream())
         self.comm.wait_event(ready)
+        marks = []
+
+        def mark():
+            if self.timing is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record(self.comm)
+                marks.append(e)
+        peers = sorted(self.peer_bufs)
         with torch.cuda.stream(self.comm):
-            self._barrier()                                           # every rank's copy of the bucket is complete
-            lo, hi = self._shard(start, end, self.rank)
-            n = hi - lo
-            n4 = (n + 3) // 4 * 4                                     # the padding past `end` belongs to nobody else
-            if n > 0:
-                for i, p in enumerate(sorted(self.peer_bufs)):
-                    self.scratch[i * self.max_shard:i * self.max_shard + n4].copy_(self.peer_bufs[p][lo:lo + n4], non_blocking=True)
-                ops.shard_mean(flat[lo:lo + n4], self.scratch, self.max_shard, self.world - 1, 1.0 / self.world, max_ctas=32)
-            self._barrier()                                           # every owner has reduced its shard
-            for p in sorted(self.peer_bufs):
-                plo, phi = self._shard(start, end, p)
-                if phi > plo:
-                    flat[plo:phi].copy_(self.peer_bufs[p][plo:phi], non_blocking=True)
+            mark()
+            self._barrier()                                           # every rank's copy of these ranges is complete
+            mark()
+            mine, off = [], 0
+            for start, end in ranges:                                 # pull my shard of every range from every peer
+                lo, hi = self._shard(start, end, self.rank)
+                n = hi - lo
+                if n <= 0:
+                    continue
+                if (len(peers) - 1) * self.max_shard + off + n > self.scratch.numel():
+                    raise RuntimeError("PeerGradSync: scratch too small for this set of ranges")
+                for i, p in enumerate(peers):
+                    self.scratch[i * self.max_shard + off:i * self.max_shard + off + n].copy_(self.peer_bufs[p][lo:hi], non_blocking=True)
+                mine.append((lo, n, off))
+                off += n
+            mark()
+            for lo, n, o in mine:
+                ops.shard_mean(flat[lo:lo + n], self.scratch[o:], self.max_shard, self.world - 1, 1.0 / self.world,
+                               max_ctas=self.mean_ctas)
+            mark()
+            self._barrier()                                           # every owner has reduced its shards
+            mark()
+            for start, end in ranges:                                 # pull the other ranks' reduced shards
+                for p in peers:
+                    plo, phi = self._shard(start, end, p)
+                    if phi > plo:
+                        flat[plo:phi].copy_(self.peer_bufs[p][plo:phi], non_blocking=True)
+            mark()
             self._last = torch.cuda.Event()
             self._last.record(self.comm)
+        if self.timing is not None:
+            self.timing.append((ranges[0][0], ranges[0][0] + sum(e - s for s, e in ranges), ready, marks))
 
     def rest_ready(self) -> None:
-        for s, e in self.rest_ranges:
-            self._reduce(s, e)
+        self._reduce_many(self._final_ranges())
         with torch.cuda.stream(self.comm):
             self._barrier()       # nobody may reuse (zero, overwrite) its gradient buffer while a peer still pulls from it
             self._last = torch.cuda.Event()
