@@ -343,6 +343,10 @@ def run_ours(args):
     if world > 1:
         broadcast_parameters(model)
         (PeerGradSync if args.sync == "peer" else GradSync).attach(model, layers_per_bucket=args.layers_per_bucket)
+    elif os.environ.get("VITK_BENCH_SEGMENTED") == "1":
+        # diagnostic: one GPU running the N>1 launch plan (backward cut into graph segments at the bucket boundaries, host
+        # callbacks in between) with nothing to communicate — isolates what the segmentation itself costs
+        GradSync.attach(model, layers_per_bucket=args.layers_per_bucket)
     opt = pkg.VitkAdamW(model, lr=2e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, max_grad_norm=1.0)
 
     g = torch.Generator().manual_seed(1 + rank)
@@ -575,7 +579,7 @@ def main():
                     help="after the K timed steps, keep stepping for this long and report it as `sustained` (0 = skip)")
     ap.add_argument("--graph", action="store_true", help="replay the step from a captured CUDA graph (chest_x_ray_vit_b200.graph)")
     ap.add_argument("--layers-per-bucket", type=lambda v: [int(x) for x in v.split(",")], default=[3, 3, 3, 2, 1], help="encoder layers per all-reduce bucket, in the order layers finish backward; last entry repeats (3 layers = 85 MB; tapered so the all-reduce left after backward is short)")
-    ap.add_argument("--sync", default="peer", choices=["peer", "nccl"],
+    ap.add_argument("--sync", default="nccl", choices=["peer", "nccl"],
                     help="gradient all-reduce at N>1: copy engines over NVLink peer memory (PeerGradSync) or NCCL (GradSync)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
