@@ -44,6 +44,7 @@ class _Plan:
         self._warm = set()
         self._keep = []      # keeps GemmArgs structs alive
         self._side = 0
+        self.sync_points: List[Tuple[torch.cuda.Event, Callable]] = []
 
     def side(self, on: bool):
         """Steps added while on=True are launched on the engine's side stream (weight-gradient work that only the
@@ -87,6 +88,15 @@ class _Plan:
     def call(self, fn: Callable[[], None]):
         self.steps.append((None, (fn,), "python"))
 
+    def sync_point(self, after: Callable[[torch.cuda.Event], None]) -> None:
+        """Everything enqueued on the main stream so far is marked by an EXTERNAL event (an event-record node when the
+        plan is replayed as a CUDA graph — the graph is not cut), and ``after(event)`` is called on the host once the whole
+        plan has been enqueued: the gradient sync then makes its communication stream wait for the event.  The bucket
+        boundaries of data-parallel training cost no graph segmentation and no host callback in the middle of backward."""
+        ev = torch.cuda.Event(external=True, enable_timing=os.environ.get("VITK_SYNC_TIMING") == "1")   # timing: tools/peer_sync_probe.py
+        self.steps.append((None, (ev,), "record"))
+        self.sync_points.append((ev, after))
+
     def _run_range(self, lo: int, hi: int, stream: int, side_stream: Optional[torch.cuda.Stream], run_py: bool = True):
         streams = {1: side_stream, 2: self.tail_stream}
         handles = {k: (v.cuda_stream if v is not None else stream) for k, v in streams.items()}
@@ -96,6 +106,8 @@ class _Plan:
                 if name == "python":
                     if run_py:
                         args[0]()
+                elif name == "record":
+                    args[0].record(torch.cuda.current_stream())
                 elif streams[args[0]] is not None:
                     other = streams[args[0]]
                     main = torch.cuda.current_stream()
@@ -119,6 +131,12 @@ class _Plan:
         plan costs one cudaGraphLaunch per segment instead of one ctypes call + cudaLaunchKernelEx per kernel
         (≈140 per plan).  ``callbacks=False`` skips the Python callbacks (no gradient sync attached): one segment.
         VITK_PLAN_GRAPHS=0 keeps the kernel-by-kernel path."""
+        self._enqueue(stream, side_stream, callbacks)
+        if callbacks:
+            for ev, after in self.sync_points:
+                after(ev)
+
+    def _enqueue(self, stream: int, side_stream: Optional[torch.cuda.Stream], callbacks: bool):
         if not _PLAN_GRAPHS or torch.cuda.is_current_stream_capturing():
             self._run_range(0, len(self.steps), stream, side_stream, callbacks)
             return
@@ -267,7 +285,7 @@ class Arena:
         T, P, B, M = cfg.seq_len, cfg.num_patches, self.B, self.M
         scale = 64 ** -0.5
         pl = _Plan()
-        # host callbacks (= breaks between CUDA-graph segments) only where the gradient sync completes a bucket
+        # one external-event sync point per gradient bucket (no host callback, no break in the CUDA graph)
         ends = eng.grad_sync.bucket_end_layers() if eng.grad_sync is not None else set()
         done_hi = [L - 1]
 
@@ -275,7 +293,7 @@ class Arena:
             if l in ends:
                 lo, hi = l, done_hi[0]
                 done_hi[0] = l - 1
-                pl.call(lambda lo=lo, hi=hi: eng._layers_grads_ready(lo, hi))
+                pl.sync_point(lambda ev, lo=lo, hi=hi: eng._layers_grads_ready(lo, hi, ev))
         mc = eng.comm_reserved_ctas()         # GEMMs of the backward leave SMs to the overlapped all-reduce
         _gemm = pl.gemm
 
@@ -361,7 +379,7 @@ class Arena:
         pl.add("vitk_embed_bwd", _p(dh), B, T, D, _p(g["pos"]), _p(g["cls"]), _p(g["bp"]), _p(self.dpatch))
         pl.gemm(self.dpatch, self.apatch, D, 768, B * P, g["wp"], EPI_ACCUM_F32, a_mn=True, b_mn=True)
         if eng.grad_sync is not None:
-            pl.call(lambda: eng._rest_grads_ready())
+            pl.sync_point(lambda ev: eng._rest_grads_ready(ev))
         return pl
 
 
@@ -523,10 +541,10 @@ class Engine:
         return tuple((chunks[i].view(sh) if chunks[i].numel() == k else chunks[i][:k].view(sh)) if nd else None
                      for (i, k, sh), nd in zip(self._spans, needs))
 
-    def _layers_grads_ready(self, lo: int, hi: int) -> None:
+    def _layers_grads_ready(self, lo: int, hi: int, ev=None) -> None:
         if self.grad_sync is not None:
-            self.grad_sync.layers_ready(lo, hi)
+            self.grad_sync.layers_ready(lo, hi, after=ev)
 
-    def _rest_grads_ready(self) -> None:
+    def _rest_grads_ready(self, ev=None) -> None:
         if self.grad_sync is not None:
-            self.grad_sync.rest_ready()
+            self.grad_sync.rest_ready(after=ev)

@@ -37,6 +37,8 @@ class GradSync:
         self.bytes_reduced = 0
         self.collectives = 0
         self._deferred: Optional[Tuple[int, int]] = None
+        self._after = None                # event after which the ranges being reduced are complete (None: current stream)
+        self._aux: Optional[torch.cuda.Stream] = None
 
     @classmethod
     def attach(cls, model, process_group=None, layers_per_bucket=3) -> "GradSync":
@@ -55,9 +57,11 @@ class GradSync:
         self.bucket_index = 0
         self._deferred = None
 
-    def layer_ready(self, l: int) -> None:
+    def layer_ready(self, l: int, after=None) -> None:
         """Layer ``l``'s weight gradients are enqueued on the current stream (layers finish in
-        descending order).  Adjacent layers are coalesced into one contiguous bucket."""
+        descending order) — or, with ``after`` (a CUDA event), are complete once that event has fired.  Adjacent layers
+        are coalesced into one contiguous bucket."""
+        self._after = after
         self.pending.append(l)
         size = self.bucket_sizes[min(self.bucket_index, len(self.bucket_sizes) - 1)]
         if len(self.pending) >= size or l == 0:
@@ -84,10 +88,12 @@ class GradSync:
                 pending, bi = 0, bi + 1
         return ends
 
-    def layers_ready(self, lo: int, hi: int) -> None:
-        """Layers lo … hi (inclusive; a whole bucket) have their weight gradients enqueued on the current stream."""
+    def layers_ready(self, lo: int, hi: int, after=None) -> None:
+        """Layers lo … hi (inclusive; a whole bucket) have their weight gradients enqueued on the current stream, or are
+        complete once the event ``after`` has fired (the engine's launch plan records it between the bucket's last
+        weight-gradient GEMM and the next layer; as an external event it is a node of the backward CUDA graph)."""
         for l in range(hi, lo - 1, -1):
-            self.layer_ready(l)
+            self.layer_ready(l, after)
 
     def _final_ranges(self) -> List[Tuple[int, int]]:
         """The deferred last layer bucket and the non-layer ranges, adjacent ones coalesced."""
@@ -101,7 +107,8 @@ class GradSync:
                 out.append((s, e))
         return out
 
-    def rest_ready(self) -> None:
+    def rest_ready(self, after=None) -> None:
+        self._after = after
         self._reduce_many(self._final_ranges())
         self.wait()
 
@@ -122,7 +129,16 @@ class GradSync:
         self.bytes_reduced += t.numel() * t.element_size()
         self.collectives += 1
         if t.is_cuda:
-            self.works.append(dist.all_reduce(t, op=dist.ReduceOp.AVG, group=self.pg, async_op=True))
+            if self._after is not None:
+                # issue from an auxiliary stream that waits for the bucket's event: NCCL's own stream then depends on the
+                # event, not on everything the main stream has been given since (the rest of backward)
+                if self._aux is None:
+                    self._aux = torch.cuda.Stream(device=t.device)
+                self._aux.wait_event(self._after)
+                with torch.cuda.stream(self._aux):
+                    self.works.append(dist.all_reduce(t, op=dist.ReduceOp.AVG, group=self.pg, async_op=True))
+            else:
+                self.works.append(dist.all_reduce(t, op=dist.ReduceOp.AVG, group=self.pg, async_op=True))
         else:   # gloo (CPU tests) has no AVG
             w = dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
             w.wait()
@@ -216,8 +232,11 @@ class PeerGradSync(GradSync):
         flat = self.sym
         self.bytes_reduced += sum(e - s for s, e in ranges) * 4
         self.collectives += 1
-        ready = torch.cuda.Event(enable_timing=self.timing is not None)
-        ready.record(torch.cuda.current_stream())
+        if self._after is not None:
+            ready = self._after
+        else:
+            ready = torch.cuda.Event(enable_timing=self.timing is not None)
+            ready.record(torch.cuda.current_stream())
         self.comm.wait_event(ready)
         marks = []
 
@@ -261,7 +280,8 @@ class PeerGradSync(GradSync):
         if self.timing is not None:
             self.timing.append((ranges[0][0], ranges[0][0] + sum(e - s for s, e in ranges), ready, marks))
 
-    def rest_ready(self) -> None:
+    def rest_ready(self, after=None) -> None:
+        self._after = after
         self._reduce_many(self._final_ranges())
         with torch.cuda.stream(self.comm):
             self._barrier()       # nobody may reuse (zero, overwrite) its gradient buffer while a peer still pulls from it

@@ -1,5 +1,6 @@
 """Per-bucket phase timing of PeerGradSync inside a real training step (run under torchrun, N >= 2)."""
 import os, sys, torch, torch.distributed as dist
+os.environ["VITK_SYNC_TIMING"] = "1"      # the plan's bucket events carry timestamps
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import chest_x_ray_vit_b200 as pkg
 from chest_x_ray_vit_b200.parallel import PeerGradSync, broadcast_parameters
