@@ -45,11 +45,14 @@ _PROTOS = {
     "vitk_patchify_u8": (C.c_int, [_p, _i64, _i64, _i64, _i64, C.POINTER(C.c_float), C.POINTER(C.c_float), _p, _p]),
     "vitk_patchify_f32": (C.c_int, [_p, _i64, _i64, _i64, _i64, _p, _p]),
     "vitk_layernorm_fwd": (C.c_int, [_p, _i64, _p, _p, _f, _i64, _i64, _p, _p, _p, _p]),
+    "vitk_layernorm_fwd_rows": (C.c_int, [_p, _i64, _p, _p, _f, _i64, _i64, _i64, _p, _p, _p, _p]),
     "vitk_layernorm_bwd": (C.c_int, [_p, _p, _i64, _p, _p, _p, _p, _i64, _i64, _p, _p, _p, _p, _p]),
     "vitk_layernorm_bwd_rows": (C.c_int, [_p, _p, _i64, _p, _p, _p, _p, _i64, _i64, _i64, _p, _p, _p, _p, _p]),
     "vitk_gemm_bf16": (C.c_int, [C.POINTER(GemmArgs), _p]),
     "vitk_colsum_bf16": (C.c_int, [_p, _i64, _i64, _i64, _p, _p]),
     "vitk_attn_fwd": (C.c_int, [_p, _i64, _i64, _i64, _f, _p, _p, _p]),
+    "vitk_attn_cls_fwd": (C.c_int, [_p, _i64, _i64, _i64, _f, _p, _p, _p]),
+    "vitk_attn_cls_bwd": (C.c_int, [_p, _p, _p, _p, _i64, _i64, _i64, _f, _p, _p]),
     "vitk_attn_bwd_workspace_bytes": (_sz, [_i64, _i64, _i64]),
     "vitk_attn_bwd": (C.c_int, [_p, _p, _p, _p, _i64, _i64, _i64, _f, _p, _p, _p]),
     "vitk_embed_cls": (C.c_int, [_p, _p, _i64, _i64, _i64, _p, _p]),

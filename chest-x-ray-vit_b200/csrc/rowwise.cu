@@ -93,8 +93,10 @@ __global__ void __launch_bounds__(256) patchify_f32_kernel(const float* __restri
 template <int VPL>
 __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restrict__ x, long long ldx,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                            float eps, int M, __nv_bfloat16* __restrict__ y,
+                                                            float eps, int M, long long rs, __nv_bfloat16* __restrict__ y,
                                                             float* __restrict__ mean, float* __restrict__ rstd) {
+  // rs: logical row r is written to physical row r·rs of y / mean / rstd (x has its own ldx); rs = T keeps the CLS rows
+  // of a [B,T,D] tensor in place
   constexpr int D = VPL * 128;
   pdl_wait();
   pdl_launch_dependents();
@@ -118,10 +120,10 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
   }
   const float r = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
   if (lane == 0) {
-    if (mean) mean[row] = mu;
-    if (rstd) rstd[row] = r;
+    if (mean) mean[row * rs] = mu;
+    if (rstd) rstd[row * rs] = r;
   }
-  uint2* yr = reinterpret_cast<uint2*>(y + static_cast<long long>(row) * D);
+  uint2* yr = reinterpret_cast<uint2*>(y + static_cast<long long>(row) * rs * D);
   const float4* g4 = reinterpret_cast<const float4*>(gamma);
   const float4* b4 = reinterpret_cast<const float4*>(beta);
 #pragma unroll
@@ -336,9 +338,9 @@ __global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float4* __rest
 }
 
 template <int VPL>
-static int ln_fwd_launch(const float* x, long long ldx, const float* gamma, const float* beta, float eps, int M,
+static int ln_fwd_launch(const float* x, long long ldx, const float* gamma, const float* beta, float eps, int M, long long rs,
                          __nv_bfloat16* y, float* mean, float* rstd, cudaStream_t s) {
-  VITK_CUDA(launch_pdl(layernorm_fwd_kernel<VPL>, dim3((M + 7) / 8), dim3(256), 0, s, x, ldx, gamma, beta, eps, M, y, mean, rstd));
+  VITK_CUDA(launch_pdl(layernorm_fwd_kernel<VPL>, dim3((M + 7) / 8), dim3(256), 0, s, x, ldx, gamma, beta, eps, M, rs, y, mean, rstd));
   VITK_LAUNCH_CHECK("layernorm_fwd_kernel");
   return 0;
 }
@@ -394,22 +396,29 @@ extern "C" VITK_API int vitk_patchify_f32(const float* pix, int64_t B, int64_t H
   return 0;
 }
 
-extern "C" VITK_API int vitk_layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps,
-                                  int64_t M, int64_t D, void* y, float* mean, float* rstd, vitk_stream_t stream) {
+extern "C" VITK_API int vitk_layernorm_fwd_rows(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps,
+                                       int64_t M, int64_t D, int64_t row_stride, void* y, float* mean, float* rstd,
+                                       vitk_stream_t stream) {
   VITK_REQUIRE(x && gamma && beta && y, VITK_EINVAL, "layernorm_fwd: NULL argument");
-  VITK_REQUIRE(M > 0 && M < (1ll << 31), VITK_EINVAL, "layernorm_fwd: bad M");
+  VITK_REQUIRE(M > 0 && M < (1ll << 31) && row_stride >= 1, VITK_EINVAL, "layernorm_fwd: bad M / row_stride");
   VITK_REQUIRE(ldx >= D && ldx % 4 == 0 && aligned16(x) && aligned16(y) && aligned16(gamma) && aligned16(beta),
                VITK_EALIGN, "layernorm_fwd: alignment");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   __nv_bfloat16* yy = static_cast<__nv_bfloat16*>(y);
+  const long long rs = row_stride;
   switch (D) {
-    case 128: return ln_fwd_launch<1>(x, ldx, gamma, beta, eps, (int)M, yy, mean, rstd, s);
-    case 256: return ln_fwd_launch<2>(x, ldx, gamma, beta, eps, (int)M, yy, mean, rstd, s);
-    case 512: return ln_fwd_launch<4>(x, ldx, gamma, beta, eps, (int)M, yy, mean, rstd, s);
-    case 768: return ln_fwd_launch<6>(x, ldx, gamma, beta, eps, (int)M, yy, mean, rstd, s);
-    case 1024: return ln_fwd_launch<8>(x, ldx, gamma, beta, eps, (int)M, yy, mean, rstd, s);
+    case 128: return ln_fwd_launch<1>(x, ldx, gamma, beta, eps, (int)M, rs, yy, mean, rstd, s);
+    case 256: return ln_fwd_launch<2>(x, ldx, gamma, beta, eps, (int)M, rs, yy, mean, rstd, s);
+    case 512: return ln_fwd_launch<4>(x, ldx, gamma, beta, eps, (int)M, rs, yy, mean, rstd, s);
+    case 768: return ln_fwd_launch<6>(x, ldx, gamma, beta, eps, (int)M, rs, yy, mean, rstd, s);
+    case 1024: return ln_fwd_launch<8>(x, ldx, gamma, beta, eps, (int)M, rs, yy, mean, rstd, s);
     default: return set_error(VITK_EINVAL, "layernorm_fwd: hidden size %lld unsupported (128,256,512,768,1024)", (long long)D);
   }
+}
+
+extern "C" VITK_API int vitk_layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps,
+                                  int64_t M, int64_t D, void* y, float* mean, float* rstd, vitk_stream_t stream) {
+  return vitk_layernorm_fwd_rows(x, ldx, gamma, beta, eps, M, D, 1, y, mean, rstd, stream);
 }
 
 extern "C" VITK_API int vitk_layernorm_bwd(const void* dy, const float* x, int64_t ldx, const float* mean, const float* rstd,

@@ -253,6 +253,10 @@ class Arena:
         pl.add("vitk_embed_cls", _p(w["cls"]), _p(w["pos"]), B, T, D, _p(h0))
         pl.gemm(self.apatch, w["wp16"], B * P, D, 768, h0, EPI_PATCH_F32, bias=w["bp"], aux=w["pos"], rows_in=P, rows_out=T,
                 row_off=1, ldd=D, ld_aux=D)
+        def cls_rows(t: torch.Tensor) -> torch.Tensor:      # the B CLS rows of a [B·T, width] buffer, in place (row stride T·width)
+            width = t.shape[1]
+            return t.view(B, T * width)[:, :width]
+
         for l in range(L):
             i = l if self.train else 0
             hin = self.h[l] if self.train else self.h[0]
@@ -262,6 +266,22 @@ class Arena:
             st = self.st[i]
             pl.add("vitk_layernorm_fwd", _p(hin), D, _p(lw["g1"]), _p(lw["b1"]), eps, M, D, _p(self.n1[i]), _p(st[0]), _p(st[1]))
             pl.gemm(self.n1[i], lw["wqkv16"], M, 3 * D, D, self.qkv[i], EPI_BIAS_BF16, bias=lw["bqkv"])
+            if l == L - 1 and eng.cls_only_top:
+                # ---- top layer: the classifier reads sequence_output[:, 0] only (HF modeling_vit.py:641), so after the keys
+                # and values of all tokens exist, everything else of this layer is computed for the B CLS rows alone —
+                # attention of one query per head, then out-proj / LN / MLP on strided [B, ·] views that leave the rows
+                # where the (CLS-only) backward of this layer expects them.  Dead rows are never read; FLOPs in bench.py
+                # stay on the dense convention.
+                pl.add("vitk_attn_cls_fwd", _p(self.qkv[i]), B, T, H, scale, _p(self.o[i]), _p(self.lse[i]))
+                o_c, hin_c, h1_c, hout_c = cls_rows(self.o[i]), cls_rows(hin), cls_rows(h1), cls_rows(hout)
+                n2_c, a_c = cls_rows(self.n2[i]), cls_rows(self.a[i])
+                pl.gemm(o_c, lw["wo16"], B, D, D, h1_c, EPI_BIAS_RESID_F32, bias=lw["bo"], aux=hin_c)
+                pl.add("vitk_layernorm_fwd_rows", _p(h1), T * D, _p(lw["g2"]), _p(lw["b2"]), eps, B, D, T, _p(self.n2[i]),
+                       _p(st[2]), _p(st[3]))
+                pl.gemm(n2_c, lw["w1_16"], B, Fi, D, a_c, EPI_BIAS_GELUG_BF16, d2=cls_rows(self.gp[i]) if self.train else None,
+                        bias=lw["bf1"])
+                pl.gemm(a_c, lw["w2_16"], B, D, Fi, hout_c, EPI_BIAS_RESID_F32, bias=lw["bf2"], aux=h1_c)
+                continue
             pl.add("vitk_attn_fwd", _p(self.qkv[i]), B, T, H, scale, _p(self.o[i]), _p(self.lse[i]))
             pl.gemm(self.o[i], lw["wo16"], M, D, D, h1, EPI_BIAS_RESID_F32, bias=lw["bo"], aux=hin)
             pl.add("vitk_layernorm_fwd", _p(h1), D, _p(lw["g2"]), _p(lw["b2"]), eps, M, D, _p(self.n2[i]), _p(st[2]), _p(st[3]))
@@ -327,10 +347,14 @@ class Arena:
         pl.add("vitk_layernorm_bwd_rows", _p(self.dn), _p(self.h1[l]), T * D, _p(st[2]), _p(st[3]), _p(lw["g2"]), _p(dh), B, D, T,
                _p(dh1), _p(lg["g2"]), _p(lg["b2"]), _p(lg["bo"]))
         pl.gemm(dh1_c, o_c, D, D, B, lg["wo"], EPI_ACCUM_F32, a_mn=True, b_mn=True)
-        pl.add("vitk_fill_zero", _p(self.do), self.do.numel() * 2)
-        pl.gemm(dh1_c, lw["wo16"], B, D, D, do_c, EPI_STORE_BF16, b_mn=True)
-        pl.add("vitk_attn_bwd", _p(self.qkv[l]), _p(self.o[l]), _p(self.do), _p(self.lse[l]), B, T, H, scale,
-               _p(self.dqkv), _p(self.attn_ws))
+        if eng.cls_only_top:
+            pl.gemm(dh1_c, lw["wo16"], B, D, D, do_c, EPI_STORE_BF16, b_mn=True)
+            pl.add("vitk_attn_cls_bwd", _p(self.qkv[l]), _p(self.o[l]), _p(self.do), _p(self.lse[l]), B, T, H, scale, _p(self.dqkv))
+        else:
+            pl.add("vitk_fill_zero", _p(self.do), self.do.numel() * 2)
+            pl.gemm(dh1_c, lw["wo16"], B, D, D, do_c, EPI_STORE_BF16, b_mn=True)
+            pl.add("vitk_attn_bwd", _p(self.qkv[l]), _p(self.o[l]), _p(self.do), _p(self.lse[l]), B, T, H, scale,
+                   _p(self.dqkv), _p(self.attn_ws))
         pl.gemm(self.dqkv, self.n1[l], 3 * D, D, M, lg["wqkv"], EPI_ACCUM_F32, a_mn=True, b_mn=True)
         pl.add("vitk_colsum_bf16", _p(self.dqkv), M, 3 * D, 3 * D, _p(lg["bqkv"]))
         pl.gemm(self.dqkv, lw["wqkv16"], M, D, 3 * D, self.dn, EPI_STORE_BF16, b_mn=True)
@@ -392,6 +416,8 @@ class Engine:
         self.arenas: Dict[Tuple[int, bool], Arena] = {}
         self.grad_sync = None            # parallel.GradSync, set by the caller for N>1
         self.side_stream = torch.cuda.Stream(device=self.dev) if os.environ.get("VITK_SIDE_STREAM", "1") != "0" else None
+        # top encoder layer computed for the CLS rows only (forward and backward); VITK_CLS_ONLY_TOP=0 runs it densely
+        self.cls_only_top = os.environ.get("VITK_CLS_ONLY_TOP", "1") != "0"
         self.w = self._weight_views(model.flat_parameters(), model.shadow())
         self.g = self._weight_views(model.flat_grads(), None)
         self._g_stage = None

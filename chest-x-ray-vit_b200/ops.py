@@ -171,6 +171,21 @@ def attn_bwd(qkv, o, do, lse, B: int, T: int, H: int, scale: float, dqkv: Option
     return dqkv
 
 
+def attn_cls_fwd(qkv: torch.Tensor, B: int, T: int, H: int, scale: float, o: torch.Tensor, lse: torch.Tensor):
+    """Attention of the CLS query only (top encoder layer): writes o[b,0,:] and lse[b,:,0]."""
+    _lib.check(_lib.lib().vitk_attn_cls_fwd(qkv.data_ptr(), B, T, H, scale, o.data_ptr(), lse.data_ptr(), _stream()), "attn_cls_fwd")
+    return o, lse
+
+
+def attn_cls_bwd(qkv, o, do, lse, B: int, T: int, H: int, scale: float, dqkv: Optional[torch.Tensor] = None):
+    """Backward of attn_cls_fwd: reads do / o at token 0 only; dqkv dense (dQ zero except token 0)."""
+    if dqkv is None:
+        dqkv = torch.empty((B * T, 3 * H * 64), dtype=bf16, device=qkv.device)
+    _lib.check(_lib.lib().vitk_attn_cls_bwd(qkv.data_ptr(), o.data_ptr(), do.data_ptr(), lse.data_ptr(), B, T, H, scale,
+                                             dqkv.data_ptr(), _stream()), "attn_cls_bwd")
+    return dqkv
+
+
 # ----------------------------------------------------------------------------- embeddings glue
 def embed_cls(cls: torch.Tensor, pos: torch.Tensor, B: int, T: int, D: int, h: torch.Tensor):
     _lib.check(_lib.lib().vitk_embed_cls(cls.data_ptr(), pos.data_ptr(), B, T, D, h.data_ptr(), _stream()), "embed_cls")

@@ -58,6 +58,10 @@ VITK_API int vitk_patchify_f32(const float* pixel_values, int64_t B, int64_t H, 
 /* ------------------------------------------------------------------ LayerNorm
  * Replaces aten::native_layer_norm / native_layer_norm_backward (HF:325-326,333,340,455).
  * x fp32 [M,D] (row stride ldx elements) → y bf16 [M,D]; mean/rstd fp32 [M] saved for backward. */
+/* (_rows: logical row r is written to physical row r·row_stride of y / mean / rstd — row_stride = T normalises the CLS
+ * rows of a [B,T,D] tensor in place, as vitk_layernorm_bwd_rows reads them.) */
+VITK_API int vitk_layernorm_fwd_rows(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps, int64_t M,
+                  int64_t D, int64_t row_stride, void* y_bf16, float* mean, float* rstd, vitk_stream_t stream);
 VITK_API int vitk_layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps,
                        int64_t M, int64_t D, void* y_bf16, float* mean, float* rstd, vitk_stream_t stream);
 /* dx = dres + LNbwd(dy) (bf16 [M,D]; dres may be NULL); dgamma/dbeta fp32 [D] are ACCUMULATED
@@ -164,6 +168,15 @@ VITK_API int vitk_head_bwd(const float* h, const float* mean, const float* rstd,
                   const float* Wc, int64_t B, int64_t T, int64_t D, int64_t C, const float* dlogits,
                   const float* dloss, void* dh_bf16, float* dWc, float* dbc, float* dgamma, float* dbeta,
                   vitk_stream_t stream);
+
+/* CLS-row attention for the top encoder layer of a classifier: HF reads only sequence_output[:, 0]
+ * (modeling_vit.py:641), so of the last layer's attention only query 0 is consumed and only its row carries a gradient.
+ * Same buffers as vitk_attn_fwd / vitk_attn_bwd; o / lse / do are touched at token 0 only; dqkv gets dense dK and dV
+ * (rank one per key), dQ at token 0 and zeros elsewhere.  T <= 8192. */
+VITK_API int vitk_attn_cls_fwd(const void* qkv_bf16, int64_t B, int64_t T, int64_t H, float scale, void* o_bf16, float* lse,
+                  vitk_stream_t stream);
+VITK_API int vitk_attn_cls_bwd(const void* qkv_bf16, const void* o_bf16, const void* do_bf16, const float* lse, int64_t B,
+                  int64_t T, int64_t H, float scale, void* dqkv_bf16, vitk_stream_t stream);
 
 /* ------------------------------------------------------------------ evaluation counters
  * Replaces compute_metrics / the final report of /root/reference/ViT-Training.py:112-118,139-146

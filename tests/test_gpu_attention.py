@@ -80,3 +80,38 @@ def test_attention_reference_maximum_jumps(ops):
     assert torch.isfinite(o.float()).all() and torch.isfinite(lse).all()
     assert (o.view(B, T, -1).float() - o_ref).abs().max() <= 3e-2 * o_ref.abs().max()
     assert torch.allclose(lse, lse_ref, atol=5e-2, rtol=2e-3)
+
+
+@pytest.mark.parametrize("B,T,H", [(2, 17, 2), (3, 197, 12), (2, 577, 12), (1, 1024, 3)])
+def test_cls_row_attention_matches_dense_and_fp32(ops, B, T, H):
+    """Top-layer kernels (one query per head): forward against the dense flash kernel's row 0 and the fp32 reference,
+    backward against the dense backward fed a gradient that is zero except on the CLS rows."""
+    g = torch.Generator().manual_seed(100 + T + H)
+    qkv = torch.randn(B, T, 3, H, 64, generator=g).to(dev).to(bf16)
+    scale = 0.125
+    do = torch.zeros(B, T, H * 64)
+    do[:, 0] = torch.randn(B, H * 64, generator=g) * 0.1
+    do = do.to(dev).to(bf16)
+    o_ref, lse_ref, dqkv_ref = _ref(qkv, do, scale)
+    o_dense, lse_dense = ops.attn_fwd(qkv, B, T, H, scale)
+    o = torch.full((B * T, H * 64), float("nan"), dtype=bf16, device=dev)        # rows other than CLS must not be needed
+    lse = torch.full((B, H, T), float("nan"), device=dev)
+    ops.attn_cls_fwd(qkv, B, T, H, scale, o, lse)
+    torch.cuda.synchronize()
+    oc = o.view(B, T, -1)[:, 0].float()
+    assert (oc - o_ref[:, 0]).abs().max() <= 2e-2 * o_ref[:, 0].abs().max()
+    assert (oc - o_dense.view(B, T, -1)[:, 0].float()).abs().max() <= 2e-2 * o_ref[:, 0].abs().max()
+    assert torch.allclose(lse[:, :, 0], lse_ref[:, :, 0], atol=2e-3, rtol=1e-4)
+    assert torch.isnan(o.view(B, T, -1)[:, 1:].float()).all() and torch.isnan(lse[:, :, 1:]).all()      # nothing else written
+    dqkv = ops.attn_cls_bwd(qkv, o, do.view(B * T, -1), lse, B, T, H, scale)
+    dense = ops.attn_bwd(qkv, o_dense, do.view(B * T, -1), lse_dense, B, T, H, scale).view(B, T, 3, H, 64).float()
+    torch.cuda.synchronize()
+    got = dqkv.view(B, T, 3, H, 64).float()
+    assert got[:, 1:, 0].abs().max() == 0                                       # dQ is zero off the CLS row
+    for i, name in enumerate("qkv"):
+        r = dqkv_ref[:, :, i]
+        err = (got[:, :, i] - r).abs().max().item()
+        cos = torch.nn.functional.cosine_similarity(got[:, :, i].flatten(), r.flatten(), dim=0).item()
+        assert err <= 3e-2 * r.abs().max().item() and cos > 0.9995, f"d{name} vs fp32: err {err} cos {cos}"
+        cosd = torch.nn.functional.cosine_similarity(got[:, :, i].flatten(), dense[:, :, i].flatten(), dim=0).item()
+        assert cosd > 0.9995, f"d{name} vs dense kernel: cos {cosd}"

@@ -63,7 +63,7 @@ def test_graphed_train_step_follows_eager_trajectory():
         la.append(out.loss.item())
         lb.append(float(gstep(x, y)))
     assert gstep.replays == 7 and gstep.kernel_launches > 0 and ob._step == oa._step == 7
-    assert la[0] == lb[0]                      # the forward is deterministic: identical kernels on identical weights
+    assert abs(la[0] - lb[0]) < 1e-6           # identical kernels on identical weights (the loss mean is an fp32 atomic sum over images)
     assert max(abs(a - b) for a, b in zip(la, lb)) < 2e-4, (la, lb)
     assert la[-1] < la[0]
 

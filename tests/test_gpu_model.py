@@ -212,7 +212,7 @@ def test_vitk_adamw_trajectory_tracks_torch_adamw():
     ob = pkg.VitkAdamW(mb, lr=lr, weight_decay=0.0, max_grad_norm=1.0)
     la = _train_steps(ma, oa, x, y, 3, clip=1.0)
     lb = _train_steps(mb, ob, x, y, 3)
-    assert la[0] == lb[0] and la[2] < la[0] and abs(la[2] - lb[2]) < 1e-4, (la, lb)
+    assert abs(la[0] - lb[0]) < 1e-6 and la[2] < la[0] and abs(la[2] - lb[2]) < 1e-4, (la, lb)   # (the loss mean is a 3-way fp32 atomic sum)
     da = torch.cat([(pa.detach() - pb.detach()).abs().flatten() for pa, pb in zip(ma.parameters(), mb.parameters())])
     frac = (da > 0.1 * lr).float().mean().item()
     print(f"trajectories after 3 steps: {100 * frac:.3f}% of elements differ by more than lr/10, mean |Δ| {da.mean().item():.2e}")
