@@ -104,7 +104,8 @@ def _(dy, x, weight, need_bias):
 def _lin_setup(ctx, inputs, output):
     x, weight, bias, gelu = inputs
     if gelu:
-        raise RuntimeError("vitk::linear with gelu=True is forward-only here; training uses the engine's fused gelu/gelu' path")
+        raise RuntimeError("vitk::linear(gelu=True) is the inference form; use vitk::linear_gelu, which also returns gelu'(u) "
+                           "for the backward pass, when gradients are needed")
     ctx.save_for_backward(x, weight)
     ctx.has_bias = bias is not None
 
@@ -116,6 +117,40 @@ def _lin_backward(ctx, dy):
 
 
 linear_op.register_autograd(_lin_backward, setup_context=_lin_setup)
+
+
+# fc1 of the MLP as one trainable op: a = gelu(x·Wᵀ + b) and g' = gelu'(x·Wᵀ + b) from ONE GEMM epilogue
+# (VITK_EPI_BIAS_GELUG_BF16, HF modeling_vit.py:296-298 + activations.py:85-86); backward is the multiplier GEMM the engine
+# uses for fc2's data gradient turned around: du = dy ∘ g' feeds vitk::linear_bwd.
+@torch.library.custom_op("vitk::linear_gelu", mutates_args=())
+def linear_gelu_op(x: Tensor, weight: Tensor, bias: Tensor) -> Tuple[Tensor, Tensor]:
+    M, K = x.shape
+    N = weight.shape[0]
+    a = torch.empty((M, N), dtype=bf16, device=x.device)
+    gp = torch.empty((M, N), dtype=bf16, device=x.device)
+    ops.gemm(x, weight, M, N, K, a, epilogue=ops.EPI_BIAS_GELUG_BF16, bias=bias, d2=gp)
+    return a, gp
+
+
+@linear_gelu_op.register_fake
+def _(x, weight, bias):
+    y = x.new_empty((x.shape[0], weight.shape[0]), dtype=bf16)
+    return y, torch.empty_like(y)
+
+
+def _lg_setup(ctx, inputs, output):
+    x, weight, bias = inputs
+    ctx.save_for_backward(x, weight, output[1])
+
+
+def _lg_backward(ctx, da, dgp):
+    x, weight, gp = ctx.saved_tensors
+    du = (da.to(bf16) * gp).contiguous()           # elementwise chain rule through the saved derivative
+    dx, dw, db = linear_bwd_op(du, x, weight, True)
+    return dx, dw.to(weight.dtype), db
+
+
+linear_gelu_op.register_autograd(_lg_backward, setup_context=_lg_setup)
 
 
 # ----------------------------------------------------------------------------- attention
@@ -170,8 +205,14 @@ class functional:
 
     @staticmethod
     def linear(x: Tensor, weight_bf16: Tensor, bias: Optional[Tensor] = None, gelu: bool = False) -> Tensor:
+        """gelu=True fuses the exact-erf GELU into the GEMM epilogue; with gradients enabled it goes through
+        vitk::linear_gelu (same epilogue, which also emits gelu'(u) for the backward pass)."""
         shp = x.shape
-        y = linear_op(x.reshape(-1, shp[-1]).to(bf16).contiguous(), weight_bf16, bias, gelu)
+        x2 = x.reshape(-1, shp[-1]).to(bf16).contiguous()
+        if gelu and bias is not None and torch.is_grad_enabled() and (x.requires_grad or weight_bf16.requires_grad or bias.requires_grad):
+            y = linear_gelu_op(x2, weight_bf16, bias)[0]
+        else:
+            y = linear_op(x2, weight_bf16, bias, gelu)
         return y.view(*shp[:-1], weight_bf16.shape[0])
 
     @staticmethod

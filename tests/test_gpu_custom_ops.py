@@ -47,9 +47,20 @@ def test_linear_op_autograd(co):
     for got, ref in ((x.grad, xr.grad), (w.grad, wr.grad), (b.grad, br.grad)):
         cos = torch.nn.functional.cosine_similarity(got.float().flatten(), ref.flatten(), dim=0).item()
         assert cos > 0.9999, cos
-    # forward-only GELU epilogue
+    # GELU epilogue: inference form ...
     yg = co.functional.linear(x.detach(), w.detach(), b.detach(), gelu=True)
     assert (yg.float() - torch.nn.functional.gelu(yr.detach())).abs().max() <= 0.03 * yr.abs().max()
+    # ... and trainable (vitk::linear_gelu: gelu and gelu' out of one epilogue, chain rule in backward)
+    x2, w2, b2 = x.detach().clone().requires_grad_(True), w.detach().clone().requires_grad_(True), b.detach().clone().requires_grad_(True)
+    ya = co.functional.linear(x2, w2, b2, gelu=True)
+    ya.backward(dy)
+    xr2, wr2, br2 = x.detach().float().requires_grad_(True), w.detach().float().requires_grad_(True), b.detach().clone().requires_grad_(True)
+    yr2 = torch.nn.functional.gelu(torch.nn.functional.linear(xr2, wr2, br2))
+    yr2.backward(dy.float())
+    assert (ya.float() - yr2).abs().max() <= 0.03 * yr2.abs().max()
+    for got, ref in ((x2.grad, xr2.grad), (w2.grad, wr2.grad), (b2.grad, br2.grad)):
+        cos = torch.nn.functional.cosine_similarity(got.float().flatten(), ref.flatten(), dim=0).item()
+        assert cos > 0.999, cos
 
 
 def test_fake_kernels_propagate_shapes(co):
