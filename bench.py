@@ -343,7 +343,22 @@ def run_ours(args):
     if world > 1:
         broadcast_parameters(model)
         sync = args.sync if args.sync != "auto" else ("peer" if world <= 4 else "nccl")
-        (PeerGradSync if sync == "peer" else GradSync).attach(model, layers_per_bucket=args.layers_per_bucket)
+        if sync == "peer":
+            # symmetric memory needs P2P mappings between all GPUs of the job: if any rank cannot set it up, every rank
+            # falls back to the NCCL sync together (the choice is agreed with a MIN all-reduce)
+            ok = 1
+            try:
+                PeerGradSync.attach(model, layers_per_bucket=args.layers_per_bucket)
+            except Exception as e:                          # noqa: BLE001
+                sys.stderr.write(f"[rank {rank}] PeerGradSync unavailable ({type(e).__name__}: {e}); using NCCL\n")
+                ok = 0
+            flag = torch.tensor([ok], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if flag.item() == 0:
+                sync = "nccl"
+                model._engine = None
+        if sync == "nccl":
+            GradSync.attach(model, layers_per_bucket=args.layers_per_bucket)
     elif os.environ.get("VITK_BENCH_SEGMENTED") == "1":
         # diagnostic: one GPU running the N>1 launch plan (backward cut into graph segments at the bucket boundaries, host
         # callbacks in between) with nothing to communicate — isolates what the segmentation itself costs

@@ -142,8 +142,11 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
 // rows with a grid stride; one smem reduction + one atomicAdd per column per block at the end.
 // rs: logical row r lives at physical row r·rs of dy / dres / dx / mean / rstd (x has its own ldx); rs = T walks
 // only the CLS rows of a [B,T,D] tensor.
+#ifndef VITK_LN_BWD_BLOCKS
+#define VITK_LN_BWD_BLOCKS 2      // resident blocks per SM the register budget is cut for (tools/build_variants.sh A/B)
+#endif
 template <int VPL>
-__global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x,
+__global__ void __launch_bounds__(256, VITK_LN_BWD_BLOCKS) layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x,
                                                                long long ldx, const float* __restrict__ mean,
                                                                const float* __restrict__ rstd, const float* __restrict__ gamma,
                                                                const __nv_bfloat16* __restrict__ dres, int M, long long rs,
@@ -350,7 +353,7 @@ static int ln_bwd_launch(const __nv_bfloat16* dy, const float* x, long long ldx,
                          float* dbeta, float* dxsum, cudaStream_t s) {
   const int warps = 8;
   const int slots = (VPL % 2 == 0) ? warps / 2 : warps;      // rows in flight per block (a warp pair per row)
-  int grid = num_sms() * 2;
+  int grid = num_sms() * VITK_LN_BWD_BLOCKS;
   const int need = (M + slots - 1) / slots;
   if (grid > need) grid = need;
   const size_t smem = static_cast<size_t>(slots) * VPL * 128 * sizeof(float);
