@@ -99,11 +99,15 @@ attn_cls_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, int T, int H, float s
   if (tid == 0) lse[(static_cast<long long>(b) * H + h) * T] = mx + logf(sum);
 }
 
-// dqkv from the gradient of the CLS row only.
+// dqkv from the gradient of the CLS row only.  Phase 1: a thread per key computes the two 64-long dot products
+// (s_j = q·K_j, dP_j = dO·V_j) and leaves p_j, dS_j in shared memory — no warp reductions on the per-key path.  Phase 2:
+// a warp per key, lanes over the head dims, writes the rank-one rows dV_j = p_j·dO and dK_j = dS_j·q coalesced and
+// accumulates dQ_cls = Σ_j dS_j·K_j in registers.
 __global__ void __launch_bounds__(kClsThreads)
 attn_cls_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ o,
                     const __nv_bfloat16* __restrict__ d_o, const float* __restrict__ lse, int T, int H, float scale,
                     __nv_bfloat16* __restrict__ dqkv) {
+  extern __shared__ float sm[];               // [T] p_j, [T] dS_j
   __shared__ float q[kClsDh], g[kClsDh], red[kClsThreads / 32], dq_part[kClsThreads / 32][kClsDh];
   pdl_wait();
   pdl_launch_dependents();
@@ -112,6 +116,8 @@ attn_cls_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
   const __nv_bfloat16* base = qkv + static_cast<long long>(b) * T * row_elems;
   __nv_bfloat16* dbase = dqkv + static_cast<long long>(b) * T * row_elems;
   const long long orow = (static_cast<long long>(b) * T * H + h) * kClsDh;      // CLS row of o / do for this head
+  float* sp = sm;
+  float* sds = sm + ((T + 3) & ~3);
   float dlt = 0.f;
   if (tid < kClsDh) {
     q[tid] = __bfloat162float(base[h * kClsDh + tid]) * scale;                  // scale folded into q
@@ -120,26 +126,23 @@ attn_cls_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
   }
   const float delta = cls_block_reduce(dlt, red, false);                         // Δ = dO·O (also publishes q, g)
   const float l = lse[(static_cast<long long>(b) * H + h) * T];
-  float dq0 = 0.f, dq1 = 0.f;                 // this lane's two head dims of dQ_cls, summed over the warp's keys
-  // a warp walks keys warp, warp+8, …; lanes split the 64 head dims two by two, the two dot products are warp sums
-  for (int j = warp; j < T; j += kClsThreads / 32) {
-    const __nv_bfloat16* krow = base + j * row_elems + (H + h) * kClsDh;
-    const __nv_bfloat16* vrow = base + j * row_elems + (2 * H + h) * kClsDh;
-    const float2 kf = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(krow)[lane]);
-    const float2 vf = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(vrow)[lane]);
-    float s = q[2 * lane] * kf.x + q[2 * lane + 1] * kf.y;
-    float dp = g[2 * lane] * vf.x + g[2 * lane + 1] * vf.y;
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      s += __shfl_xor_sync(0xffffffffu, s, off);
-      dp += __shfl_xor_sync(0xffffffffu, dp, off);
-    }
+  for (int j = tid; j < T; j += kClsThreads) {
+    const float s = dot64(q, base + j * row_elems + (H + h) * kClsDh);
+    const float dp = dot64(g, base + j * row_elems + (2 * H + h) * kClsDh);
     const float p = __expf(s - l);
-    const float ds = p * (dp - delta);
+    sp[j] = p;
+    sds[j] = p * (dp - delta);
+  }
+  __syncthreads();
+  const float q0 = q[2 * lane], q1 = q[2 * lane + 1], g0 = g[2 * lane], g1 = g[2 * lane + 1];
+  float dq0 = 0.f, dq1 = 0.f;                 // this lane's two head dims of dQ_cls, summed over the warp's keys
+  for (int j = warp; j < T; j += kClsThreads / 32) {
+    const float p = sp[j], ds = sds[j];
+    const float2 kf = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(base + j * row_elems + (H + h) * kClsDh)[lane]);
     __nv_bfloat16* drow = dbase + j * row_elems + h * kClsDh;
-    reinterpret_cast<__nv_bfloat162*>(drow + 2 * H * kClsDh)[lane] = __floats2bfloat162_rn(p * g[2 * lane], p * g[2 * lane + 1]);   // dV_j
-    reinterpret_cast<__nv_bfloat162*>(drow + H * kClsDh)[lane] = __floats2bfloat162_rn(ds * q[2 * lane], ds * q[2 * lane + 1]);     // dK_j
-    if (j > 0) reinterpret_cast<__nv_bfloat162*>(drow)[lane] = __floats2bfloat162_rn(0.f, 0.f);                                     // dQ_j = 0
+    reinterpret_cast<__nv_bfloat162*>(drow + 2 * H * kClsDh)[lane] = __floats2bfloat162_rn(p * g0, p * g1);     // dV_j
+    reinterpret_cast<__nv_bfloat162*>(drow + H * kClsDh)[lane] = __floats2bfloat162_rn(ds * q0, ds * q1);       // dK_j
+    if (j > 0) reinterpret_cast<__nv_bfloat162*>(drow)[lane] = __floats2bfloat162_rn(0.f, 0.f);                 // dQ_j = 0
     dq0 = fmaf(ds * scale, kf.x, dq0);
     dq1 = fmaf(ds * scale, kf.y, dq1);
   }
@@ -159,8 +162,8 @@ attn_cls_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
 using namespace vitk;
 
 static int cls_check(const char* who, int64_t B, int64_t T, int64_t H) {
-  VITK_REQUIRE(B > 0 && T > 0 && H > 0 && B < 65536 && H < 65536 && T <= 8192, VITK_EINVAL,
-               "%s: unsupported shape B=%lld T=%lld H=%lld (T <= 8192)", who, (long long)B, (long long)T, (long long)H);
+  VITK_REQUIRE(B > 0 && T > 0 && H > 0 && B < 65536 && H < 65536 && T <= 4096, VITK_EINVAL,
+               "%s: unsupported shape B=%lld T=%lld H=%lld (T <= 4096)", who, (long long)B, (long long)T, (long long)H);
   return 0;
 }
 
@@ -182,7 +185,8 @@ extern "C" VITK_API int vitk_attn_cls_bwd(const void* qkv, const void* o, const 
   if (int rc = cls_check("attn_cls_bwd", B, T, H)) return rc;
   VITK_REQUIRE(aligned16(qkv) && aligned16(o) && aligned16(d_o) && aligned16(dqkv) && scale > 0.f, VITK_EALIGN,
                "attn_cls_bwd: buffers must be 16-byte aligned, scale > 0");
-  VITK_CUDA(launch_pdl(attn_cls_bwd_kernel, dim3((unsigned)H, (unsigned)B), dim3(kClsThreads), 0, static_cast<cudaStream_t>(stream),
+  const size_t smem = 2 * ((T + 3) & ~3) * sizeof(float);
+  VITK_CUDA(launch_pdl(attn_cls_bwd_kernel, dim3((unsigned)H, (unsigned)B), dim3(kClsThreads), smem, static_cast<cudaStream_t>(stream),
                        static_cast<const __nv_bfloat16*>(qkv), static_cast<const __nv_bfloat16*>(o),
                        static_cast<const __nv_bfloat16*>(d_o), lse, (int)T, (int)H, scale, static_cast<__nv_bfloat16*>(dqkv)));
   VITK_LAUNCH_CHECK("attn_cls_bwd_kernel");

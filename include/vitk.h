@@ -172,7 +172,7 @@ VITK_API int vitk_head_bwd(const float* h, const float* mean, const float* rstd,
 /* CLS-row attention for the top encoder layer of a classifier: HF reads only sequence_output[:, 0]
  * (modeling_vit.py:641), so of the last layer's attention only query 0 is consumed and only its row carries a gradient.
  * Same buffers as vitk_attn_fwd / vitk_attn_bwd; o / lse / do are touched at token 0 only; dqkv gets dense dK and dV
- * (rank one per key), dQ at token 0 and zeros elsewhere.  T <= 8192. */
+ * (rank one per key), dQ at token 0 and zeros elsewhere.  T <= 4096. */
 VITK_API int vitk_attn_cls_fwd(const void* qkv_bf16, int64_t B, int64_t T, int64_t H, float scale, void* o_bf16, float* lse,
                   vitk_stream_t stream);
 VITK_API int vitk_attn_cls_bwd(const void* qkv_bf16, const void* o_bf16, const void* do_bf16, const float* lse, int64_t B,
