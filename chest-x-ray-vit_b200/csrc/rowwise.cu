@@ -145,6 +145,9 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
 #ifndef VITK_LN_BWD_BLOCKS
 #define VITK_LN_BWD_BLOCKS 2      // resident blocks per SM the register budget is cut for (tools/build_variants.sh A/B)
 #endif
+#ifndef VITK_LN_BWD_PREFETCH
+#define VITK_LN_BWD_PREFETCH 1    // 1: the next row is loaded while this one is reduced (24 more registers); 0: rely on occupancy
+#endif
 template <int VPL>
 __global__ void __launch_bounds__(256, VITK_LN_BWD_BLOCKS) layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x,
                                                                long long ldx, const float* __restrict__ mean,
@@ -186,16 +189,17 @@ __global__ void __launch_bounds__(256, VITK_LN_BWD_BLOCKS) layernorm_bwd_kernel(
       rn[i] = dres ? __ldg(reinterpret_cast<const uint2*>(dres + pr * D) + c0 + 32 * i) : make_uint2(0u, 0u);
     }
   };
-  if (row < M) fetch(row);
+  if (VITK_LN_BWD_PREFETCH && row < M) fetch(row);
   int parity = 0;
   for (; row < M; row += row_step, parity ^= 1) {
     const long long prow = static_cast<long long>(row) * rs;
     const float mu = __ldg(mean + prow), r = __ldg(rstd + prow);
+    if (!VITK_LN_BWD_PREFETCH) fetch(row);
     float4 xv[V];
     uint2 dw[V], rw_[V];
 #pragma unroll
     for (int i = 0; i < V; ++i) { xv[i] = xn[i]; dw[i] = dn[i]; rw_[i] = rn[i]; }
-    if (row + row_step < M) fetch(row + row_step);
+    if (VITK_LN_BWD_PREFETCH && row + row_step < M) fetch(row + row_step);
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < V; ++i) {
