@@ -408,7 +408,7 @@ extern "C" VITK_API int vitk_gemm_bf16(const vitk_gemm_args* args, vitk_stream_t
     VITK_REQUIRE(a.d2 != nullptr && aligned16(a.d2), VITK_EINVAL, "gemm: BIAS_GELU needs d2");
   if (a.epilogue == VITK_EPI_BIAS_GELUG_BF16 && a.d2 != nullptr)
     VITK_REQUIRE(aligned16(a.d2), VITK_EALIGN, "gemm: d2 must be 16-byte aligned");
-  VITK_REQUIRE(a.variant >= 0 && a.variant <= 2, VITK_EINVAL, "gemm: variant must be 0 (auto), 1 (single-CTA) or 2 (CTA pair)");
+  VITK_REQUIRE(a.variant >= 0 && a.variant <= 3, VITK_EINVAL, "gemm: variant must be 0 (auto), 1 (single-CTA), 2 (CTA pair) or 3 (CTA pair, 8 epilogue warps)");
   if (a.epilogue == VITK_EPI_BIAS_RESID_F32 || a.epilogue == VITK_EPI_PATCH_F32 || a.epilogue == VITK_EPI_DGELU_BF16 ||
       a.epilogue == VITK_EPI_MUL_BF16)
     VITK_REQUIRE(a.aux != nullptr && aligned16(a.aux) && a.ld_aux % 8 == 0 && a.ld_aux >= a.N, VITK_EINVAL,

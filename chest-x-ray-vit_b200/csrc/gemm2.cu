@@ -41,20 +41,24 @@ namespace vitk {
 
 constexpr int k2BM = 128;            // rows per CTA (256 per pair)
 constexpr int k2BK = 64;
-constexpr int k2EpiWarps = 8;
 constexpr int k2FirstEpiWarp = 2;
-constexpr int k2Threads = (k2FirstEpiWarp + k2EpiWarps) * 32;   // 384
+// Epilogue warps per CTA (template parameter EW): 8 by default (two per TMEM lane quadrant, each draining half of the
+// tile's columns), 16 for the GELU instantiation (four per quadrant, a quarter of the columns each): its epilogue is a
+// chain of dependent latencies (TMEM load → 2 MUFU + 13 FP32 per element → pack → shared memory → fence → TMA store)
+// that four warps per scheduler hide better than two.
+constexpr int threads2(int ew) { return (k2FirstEpiWarp + ew) * 32; }
 constexpr int k2ABytes = k2BM * k2BK * 2;                       // 16 KB
 #ifndef VITK_G2_SLABS
 #define VITK_G2_SLABS 2      // 2 and 4 measured equal (the epilogue is not waiting on its TMA stores)
 #endif
 constexpr int k2Slabs = VITK_G2_SLABS;                          // [32 rows × 64 B] slabs per epilogue warp (TMA stores in flight)
 constexpr int k2SlabBytes = k2Slabs * 2048;
-constexpr int k2StagingBytes = k2EpiWarps * k2SlabBytes;        // 32 KB
+constexpr int staging_bytes2(int ew) { return ew * k2SlabBytes; }  // 32 KB (8 warps) / 64 KB (16 warps)
+constexpr int k2MaxSmem = 227 * 1024;
 constexpr int k2BiasBytes = 2 * 2 * 128 * 4;                     // bias slice (≤128 floats) per column half × tile parity
 constexpr int k2BarBytes = 256;
 
-template <int BN>
+template <int BN, int EW = 8>
 struct Cfg2 {
   static constexpr int kBHalfRows = BN / 2;
   static constexpr int kBBytes = kBHalfRows * k2BK * 2;
@@ -65,9 +69,12 @@ struct Cfg2 {
 #ifndef VITK_G2_STAGES
 #define VITK_G2_STAGES 6     // 4, 5 and 6 measured equal: the K-block cadence is a throughput limit, not a latency one
 #endif
-  static constexpr int kStages = (BN == 256) ? VITK_G2_STAGES : (BN == 192 ? VITK_G2_STAGES : VITK_G2_STAGES + 2);
+  static constexpr int kStagingBytes = staging_bytes2(EW);
+  static constexpr int kWantStages = (BN == 256) ? VITK_G2_STAGES : (BN == 192 ? VITK_G2_STAGES : VITK_G2_STAGES + 2);
+  static constexpr int kFitStages = (k2MaxSmem - kStagingBytes - k2BiasBytes - k2BarBytes) / kStageBytes;
+  static constexpr int kStages = kWantStages < kFitStages ? kWantStages : kFitStages;   // 16 epilogue warps: 5 stages at BN = 256 / 192
   static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;
-  static constexpr int kSmemBytes = kStages * kStageBytes + k2StagingBytes + k2BiasBytes + k2BarBytes;   // no slack: smem_raw is declared 1024-aligned
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + k2BiasBytes + k2BarBytes;   // no slack: smem_raw is declared 1024-aligned
 };
 
 struct Gemm2Params {
@@ -173,8 +180,10 @@ __device__ __forceinline__ void add_bias32(const float* __restrict__ bias, int c
 // Two instantiations because the epilogue sits at the 168-register cap (10 warps, 3 per SM sub-partition): the
 // aux look-ahead registers and the GELU temporaries never coexist, and with both in one kernel ptxas spilled the
 // prefetched bias across the accumulator wait — i.e. stalled on that load once per tile.
-template <int BN, bool A_MN, bool B_MN, bool AUX>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1)
+// EW: epilogue warps (8 or 16).  EPI: compile-time epilogue (−1: taken from Gemm2Params at run time) — 18 warps put
+// five on one SM sub-partition, i.e. a 96-register cap, which only a single epilogue's code fits.
+template <int BN, bool A_MN, bool B_MN, bool AUX, int EW = 8, int EPI = -1>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(threads2(EW), 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                   const __grid_constant__ CUtensorMap tma_bh,   // K-major B, box of BN/4 rows (half-width tiles)
                   const __grid_constant__ CUtensorMap tma_d, const __grid_constant__ CUtensorMap tma_d2,
@@ -185,9 +194,13 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
 #define VITK_GEMM_STAMPS 0
 #endif
   constexpr bool kStamps = VITK_GEMM_STAMPS != 0;
-  using Cfg = Cfg2<BN>;
+  using Cfg = Cfg2<BN, EW>;
   constexpr int kStages = Cfg::kStages;
   constexpr int kBHalf = Cfg::kBHalfRows;
+  constexpr int kParts = EW / 4;                 // column parts of a tile, one per group of four (quadrant) warps
+  constexpr int kBiasPart = 256 / kParts;        // bias floats per part and tile parity
+  constexpr int k2StagingBytes = Cfg::kStagingBytes;
+  static_assert(EW == 8 || EW == 16, "epilogue warps: two or four per TMEM lane quadrant");
   if (kStamps && p.tl != nullptr && threadIdx.x == 0) {   // debug timeline: [6400 + cta] = globaltimer at kernel entry
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -224,7 +237,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], 2 * k2EpiWarps);
+      mbar_init(&acc_empty[s], 2 * EW);
     }
     fence_mbar_init();
   }
@@ -362,10 +375,10 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     // third slab, so the SM's TMA queue carries only operand loads and output stores.
     const int ew = warp - k2FirstEpiWarp;
     const int quad = warp & 3;                // TMEM lane quadrant (= warp id % 4)
-    const int col_half = ew >> 2;
+    const int part = ew >> 2;                 // which column part of the tile this warp drains
     uint8_t* slabs = staging + ew * k2SlabBytes;            // 2 × 2 KB
-    float* bias_base = reinterpret_cast<float*>(staging + k2StagingBytes) + col_half * 256;   // [tile parity][128], shared by the 4 warps of this column half
-    const int epi = p.epi;
+    float* bias_base = reinterpret_cast<float*>(staging + k2StagingBytes) + part * (2 * kBiasPart);   // [tile parity][kBiasPart], shared by the 4 warps of this column part
+    const int epi = EPI >= 0 ? EPI : p.epi;
     const bool out_f32 = epi == VITK_EPI_BIAS_RESID_F32 || epi == VITK_EPI_ACCUM_F32 || epi == VITK_EPI_STORE_F32;
     const bool has_aux = AUX && !(p.dbg & 2) && (epi == VITK_EPI_BIAS_RESID_F32 || epi == VITK_EPI_MUL_BF16 || epi == VITK_EPI_DGELU_BF16);
     const bool has_bias = p.bias != nullptr && (epi == VITK_EPI_BIAS_BF16 || epi == VITK_EPI_BIAS_GELU_BF16 ||
@@ -381,7 +394,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     const int rc = lane >> 2, jc = lane & 3;               // coalesced layout: iteration i ↔ row 8i + rc, 16-byte chunk jc
 
     auto tile_row0 = [&](const Work2& it) { return it.m_blk * (2 * k2BM) + static_cast<int>(cta_rank) * k2BM + quad * 32; };
-    auto tile_col0 = [&](const Work2& it) { return it.n0 + col_half * (it.bn >> 1); };   // this warp's column half of the tile
+    auto tile_col0 = [&](const Work2& it) { return it.n0 + part * (it.bn / kParts); };   // this warp's column part of the tile
 
     uint4 axA[4], axB[4];  // aux chunks in flight (coalesced layout); named, never indexed dynamically, so they stay in registers
     auto load_aux = [&](uint4 (&dst)[4], int row0, int col) {
@@ -395,10 +408,11 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       }
     };
     // coordinates of the chunk `ahead` (≤ 2) chunks after chunk c of tile `cur`; `nxt` is this CTA's next tile
-    // (every tile has ≥ 2 chunks, so the look-ahead never reaches past it); false when past the last tile
+    // (every tile has ≥ 2 chunks per warp — aux epilogues run with 8 epilogue warps — so the look-ahead never reaches
+    // past it); false when past the last tile
     auto chunk_after = [&](const Work2& cur, const Work2& nxt, bool has_next, int c, int ahead, int* row0, int* col) {
       c += ahead;
-      const int nch = (cur.bn >> 1) >> cshift;
+      const int nch = (cur.bn / kParts) >> cshift;
       if (c < nch) {
         *row0 = tile_row0(cur);
         *col = tile_col0(cur) + c * cw;
@@ -449,28 +463,29 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       const bool has_next = w + num_pairs < p.total_work;
       const Work2 nxt = decode_work2<BN>(p, has_next ? w + num_pairs : w);
       const int row0 = tile_row0(it), col0 = tile_col0(it);
-      const int half_w = it.bn >> 1;                       // columns of this tile that belong to this warp's column half
+      const int half_w = it.bn / kParts;                   // columns of this tile that belong to this warp's column part
       const int nchunks = half_w >> cshift;
       // This column half's BN/2 bias values: fetched before the wait, published to smem after it.  The slice is
       // shared by the 4 quadrant warps (identical values) and double-buffered by tile parity; a warp past
       // acc_full(t) knows every warp finished READING the bias of tile t−2, because those reads precede the
       // acc_empty(t−2) arrivals that MMA(t) waited for.
-      float* bias_s = bias_base + acc * 128;
-      float bpre[4];
+      float* bias_s = bias_base + acc * kBiasPart;
+      constexpr int kBiasIters = kBiasPart / 32;
+      float bpre[kBiasIters];
       if (has_bias) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) bpre[i] = (lane + 32 * i < half_w) ? __ldg(p.bias + col0 + lane + 32 * i) : 0.f;
+        for (int i = 0; i < kBiasIters; ++i) bpre[i] = (lane + 32 * i < half_w) ? __ldg(p.bias + col0 + lane + 32 * i) : 0.f;
       }
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after_sync();
       if (stamp && ew == 0 && lane == 0 && ti < 256) p.tl[4096 + 4 * ti] = clock64();
       if (has_bias) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < kBiasIters; ++i)
           if (lane + 32 * i < half_w) bias_s[lane + 32 * i] = bpre[i];
         __syncwarp();
       }
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + col_half * half_w;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + part * half_w;
 #pragma unroll 1
       for (int c = 0; c < nchunks; ++c) {
         const int col = col0 + c * cw;
@@ -641,9 +656,9 @@ static int out_map(CUtensorMap* m, const void* base, bool f32, long long rows, l
   return get_tensor_map(m, base, f32 ? TM_F32 : TM_BF16, 2, dims, str, box, TM_SW64);
 }
 
-template <int BN, bool A_MN, bool B_MN, bool AUX>
+template <int BN, bool A_MN, bool B_MN, bool AUX, int EW = 8, int EPI = -1>
 static int launch_gemm2(const vitk_gemm_args& a, const Gemm2Params& p, int pairs, cudaStream_t stream) {
-  using Cfg = Cfg2<BN>;
+  using Cfg = Cfg2<BN, EW>;
   CUtensorMap ta, tb, tbh, td, td2;
   {
     uint64_t dims[2], str[1];
@@ -666,14 +681,14 @@ static int launch_gemm2(const vitk_gemm_args& a, const Gemm2Params& p, int pairs
   if (int rc = out_map(&td, a.d, f32_out, a.M, a.N, a.ldd)) return rc;
   td2 = td;
   if (a.d2 != nullptr) { if (int rc = out_map(&td2, a.d2, false, a.M, a.N, a.ldd)) return rc; }
-  auto kern = gemm2_bf16_kernel<BN, A_MN, B_MN, AUX>;
+  auto kern = gemm2_bf16_kernel<BN, A_MN, B_MN, AUX, EW, EPI>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [&] {
     attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
   });
   if (attr_err != cudaSuccess) return cuda_error(attr_err, "cudaFuncSetAttribute(gemm2 smem)");
-  if (cudaError_t e = launch_pdl(kern, dim3(2 * pairs), dim3(k2Threads), Cfg::kSmemBytes, stream, ta, tb, tbh, td, td2, p); e != cudaSuccess)
+  if (cudaError_t e = launch_pdl(kern, dim3(2 * pairs), dim3(threads2(EW)), Cfg::kSmemBytes, stream, ta, tb, tbh, td, td2, p); e != cudaSuccess)
     return cuda_error(e, "gemm2_bf16_kernel launch");
   VITK_LAUNCH_CHECK("gemm2_bf16_kernel");
   return 0;
@@ -691,6 +706,23 @@ static int dispatch_major2(const vitk_gemm_args& a, const Gemm2Params& p, int pa
   }
   return set_error(VITK_EINVAL, "gemm2: unsupported operand layout for this tile width / epilogue (tile_n 192 needs a K-major B; "
                                 "aux epilogues need a K-major A)");
+}
+
+// fc1 forward (+bias, GELU, optional GELU') as a 16-epilogue-warp instantiation with the epilogue fixed at compile time
+// (see the kernel's template comment): 2 MUFU + 13 FP32 operations per element are a chain of dependent latencies that
+// four warps per scheduler hide better than two — 51.4 → 47.1 µs at M = 9232 (profiles/r02_bench_gemm_ew16.txt), bit-identical
+// output (tests/test_gpu_gemm.py::test_sixteen_warp_epilogues_equal_eight_warp).  The same treatment of the multiplier
+// and fp32-residual epilogues was measured and dropped: those launches move 128 / 71 MB for 43.6 / 10.9 GF and sit on
+// the HBM side of the roofline, not on the epilogue's instruction latency (no change at 49.2 / 28.7 / 47.1 µs).
+// VITK_GEMM_EW16=0 switches the instantiation off (A/B); variant 3 does the same per call.
+static bool launch_heavy2(const vitk_gemm_args& a, const Gemm2Params& p, int bn, int pairs, cudaStream_t s, int* rc) {
+  static const int on = [] { const char* e = getenv("VITK_GEMM_EW16"); return e ? atoi(e) : 1; }();
+  if (!on || a.variant == 3) return false;
+  if (a.epilogue == VITK_EPI_BIAS_GELUG_BF16 && !a.a_mn_major && !a.b_mn_major && bn == 256) {
+    *rc = launch_gemm2<256, false, false, false, 16, VITK_EPI_BIAS_GELUG_BF16>(a, p, pairs, s);
+    return true;
+  }
+  return false;
 }
 
 // cycles a CTA pair spends per 64-wide K block of a tile of `bn` columns (tools/gemm_timeline.py, B200): the MMAs of a
@@ -778,7 +810,7 @@ int gemm2_try_launch(const vitk_gemm_args& a, cudaStream_t stream, bool* handled
                         (a.tile_n == 0 || a.tile_n == 128 || a.tile_n == 192 || a.tile_n == 256) &&
                         !(a.tile_n == 192 && a.b_mn_major);
   if (!eligible) {
-    VITK_REQUIRE(a.variant != 2, VITK_EINVAL, "gemm: the CTA-pair kernel does not support this problem (epilogue %d, tile_n %d)",
+    VITK_REQUIRE(a.variant < 2, VITK_EINVAL, "gemm: the CTA-pair kernel does not support this problem (epilogue %d, tile_n %d)",
                  a.epilogue, a.tile_n);
     return 0;
   }
@@ -789,7 +821,7 @@ int gemm2_try_launch(const vitk_gemm_args& a, cudaStream_t stream, bool* handled
   double pair_cost = 0;
   choose_tiling2(a, pairs_avail, &bn, &splits, &n_half, &pair_cost);
   if (bn == 0) {
-    VITK_REQUIRE(a.variant != 2, VITK_EINVAL, "gemm: no CTA-pair tiling for N=%lld tile_n=%d", (long long)a.N, a.tile_n);
+    VITK_REQUIRE(a.variant < 2, VITK_EINVAL, "gemm: no CTA-pair tiling for N=%lld tile_n=%d", (long long)a.N, a.tile_n);
     return 0;
   }
   if (single_cta_wins(a, pair_cost, sms)) return 0;     // falls through to the single-CTA kernel (gemm.cu), 256-wide tiles
@@ -818,6 +850,10 @@ int gemm2_try_launch(const vitk_gemm_args& a, cudaStream_t stream, bool* handled
   p.tl_seq = g_timeline != nullptr ? g_timeline_seq++ : 0;
   const int pairs = p.total_work < pairs_avail ? p.total_work : pairs_avail;
   *handled = true;
+  {
+    int rc = 0;
+    if (launch_heavy2(a, p, bn, pairs, stream, &rc)) return rc;
+  }
   switch (bn) {
     case 256: return aux_epi ? dispatch_major2<256, true>(a, p, pairs, stream) : dispatch_major2<256, false>(a, p, pairs, stream);
     case 192: return aux_epi ? dispatch_major2<192, true>(a, p, pairs, stream) : dispatch_major2<192, false>(a, p, pairs, stream);

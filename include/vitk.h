@@ -122,7 +122,9 @@ typedef struct vitk_gemm_args {
   int32_t tile_n;        /* 0 = library chooses; else 128, 192 or 256 */
   int32_t max_ctas;      /* 0 = all SMs; else cap on the persistent grid, leaving SMs to a concurrent collective */
   int32_t variant;       /* 0 = library chooses; 1 = single-CTA 128×N tiles (gemm.cu); 2 = CTA pair,
-                            256×N tiles, TMA-store epilogue (gemm2.cu; not for VITK_EPI_PATCH_F32) */
+                            256×N tiles, TMA-store epilogue (gemm2.cu; not for VITK_EPI_PATCH_F32); 3 = as 2 but
+                            always with 8 epilogue warps (the A/B reference of the 16-warp heavy-epilogue
+                            instantiations, which produce the same bits) */
 } vitk_gemm_args;
 
 VITK_API int vitk_gemm_bf16(const vitk_gemm_args* args, vitk_stream_t stream);

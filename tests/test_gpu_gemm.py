@@ -203,3 +203,45 @@ def test_mixed_width_tiles_full_batch(ops, N, K, b_mn):
     ur = ref + bias
     gr = torch.nn.functional.gelu(ur)
     assert (act.float() - gr).abs().max() <= _tol(K, ur) + 2 ** -8 * gr.abs().max()
+
+
+@pytest.mark.parametrize("M", [9232, 4616, 1154, 300])
+def test_sixteen_warp_epilogues_equal_eight_warp(ops, M):
+    """fc1 + GELU (+ GELU') runs as a 16-epilogue-warp instantiation of the pair kernel; variant 3 forces the 8-warp
+    kernel on the same tiling.  Same K order, same arithmetic per element: the outputs must agree bit for bit, with and
+    without the second output, ragged last band included.  The multiplier / fp32-residual epilogues (8 warps either way)
+    ride along as a check that variant 3 changes nothing else."""
+    g = torch.Generator().manual_seed(M)
+    D, F = 768, 3072
+    x = torch.randn(M, D, generator=g).to(dev).to(bf16)
+    w1 = (torch.randn(F, D, generator=g) * 0.05).to(dev).to(bf16)
+    b1 = torch.randn(F, generator=g).to(dev) * 0.5
+    outs = {}
+    for variant in (2, 3):
+        act = torch.full((M, F), float("nan"), device=dev, dtype=bf16)
+        gp = torch.full((M, F), float("nan"), device=dev, dtype=bf16)
+        ops.gemm(x, w1, M, F, D, act, epilogue=ops.EPI_BIAS_GELUG_BF16, d2=gp, bias=b1, variant=variant, tile_n=256)
+        act1 = torch.full((M, F), float("nan"), device=dev, dtype=bf16)
+        ops.gemm(x, w1, M, F, D, act1, epilogue=ops.EPI_BIAS_GELUG_BF16, bias=b1, variant=variant, tile_n=256)   # no d2
+        # fc2 data gradient: dh [M, D] · W2 [D, F] (MN-major B) × gelu'
+        du = torch.full((M, F), float("nan"), device=dev, dtype=bf16)
+        w2 = w1.t().contiguous()                                     # stored [D, F]: element (n, k) at k·F + n
+        ops.gemm(x, w2, M, F, D, du, epilogue=ops.EPI_MUL_BF16, aux=gp, b_mn_major=True, variant=variant, tile_n=256)
+        # out-proj / fc2 forward with the fp32 residual, in place, default tiling (192-wide or mixed) and forced 256
+        wo = w1[:D].contiguous()
+        bo = b1[:D].contiguous()
+        res = torch.randn(M, D, generator=torch.Generator().manual_seed(1)).to(dev)
+        h = {}
+        for tn in (0, 192, 256):
+            h[tn] = res.clone()
+            ops.gemm(x, wo, M, D, D, h[tn], epilogue=ops.EPI_BIAS_RESID_F32, bias=bo, aux=h[tn], variant=variant, tile_n=tn)
+        h2 = res.clone()
+        ops.gemm(act, w2, M, D, F, h2, epilogue=ops.EPI_BIAS_RESID_F32, bias=bo, aux=h2, variant=variant)      # K = 3072
+        outs[variant] = (act, gp, act1, du, h[0], h[192], h[256], h2)
+    torch.cuda.synchronize()
+    names = ("gelu", "gelu'", "gelu (no d2)", "mul", "resid auto", "resid 192", "resid 256", "resid K=3072")
+    for n, a16, a8 in zip(names, outs[2], outs[3]):
+        assert not torch.isnan(a16.float()).any(), n
+        assert torch.equal(a16, a8), n
+    ref = torch.nn.functional.gelu(x.float() @ w1.float().t() + b1)
+    assert (outs[2][0].float() - ref).abs().max() <= _tol(D, ref) + 2 ** -8 * ref.abs().max()

@@ -99,6 +99,8 @@ if len(sys.argv) > 1 and sys.argv[1] == "--splitk":        # weight-gradient lau
     CASES = [c for c in CASES if "wgrad" in c["name"]]
 if len(sys.argv) > 1 and sys.argv[1] == "--auto":
     configs = [dict(variant=0), dict(variant=1)]
+if len(sys.argv) > 1 and sys.argv[1] == "--ew":          # 16-warp heavy epilogues (default) vs the 8-warp kernel (variant 3)
+    configs = [dict(variant=2), dict(variant=3)]
 if len(sys.argv) > 1 and sys.argv[1] == "--cublas":
     configs = [dict(variant=2), dict(cublas=True)]
 if len(sys.argv) > 1 and sys.argv[1] == "--none":         # imported as a module (tools/gemm_timeline.py)
