@@ -417,6 +417,69 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __
   }
 }
 
+// The same for H ≤ 16 heads (NIT = ⌈H/4⌉), organised for bandwidth: a block owns 16 consecutive (padded) token rows of
+// one image, a warp two of them with all of their O / dO loads (4·NIT × 16 B per lane) in flight at once, and the
+// per-head results cross shared memory so that lse2 / delta are written as 64-byte runs per head instead of one
+// 4-byte store per (row, head) with a Tpad·4-byte stride (which cost 37 % extra sector traffic and most of the time).
+template <int NIT>
+__global__ void __launch_bounds__(256) attn_delta16_kernel(const __nv_bfloat16* __restrict__ o,
+                                                           const __nv_bfloat16* __restrict__ d_o, const float* __restrict__ lse,
+                                                           int B, int T, int Tpad, int H, float* __restrict__ lse2,
+                                                           float* __restrict__ delta) {
+  __shared__ float sd[4 * NIT][17];                  // [head][row of the block]
+  pdl_wait();
+  pdl_launch_dependents();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row0 = blockIdx.x * 16;                  // over B·Tpad (Tpad is a multiple of 128: a block never straddles images)
+  const int b = row0 / Tpad, t0 = row0 - b * Tpad;
+  const int D = H * kDh, nchunk = D / 8;             // 16-byte chunks per row; chunk c covers columns [8c, 8c+8) of head c/8
+  uint4 a[2][NIT], g[2][NIT];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int t = t0 + 2 * warp + j;
+    const long long grow = static_cast<long long>(b) * T + t;
+    const uint4* po = reinterpret_cast<const uint4*>(o + grow * D);
+    const uint4* pd = reinterpret_cast<const uint4*>(d_o + grow * D);
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const int c = it * 32 + lane;
+      const bool ok = t < T && c < nchunk;
+      a[j][it] = ok ? __ldg(po + c) : make_uint4(0u, 0u, 0u, 0u);
+      g[j][it] = ok ? __ldg(pd + c) : make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const uint32_t aw[4] = {a[j][it].x, a[j][it].y, a[j][it].z, a[j][it].w}, gw[4] = {g[j][it].x, g[j][it].y, g[j][it].z, g[j][it].w};
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&aw[i]));
+        const float2 y = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&gw[i]));
+        s += x.x * y.x + x.y * y.y;
+      }
+      s += __shfl_xor_sync(0xffffffffu, s, 1);       // 8 consecutive lanes hold one head (same order as attn_delta_kernel)
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      s += __shfl_xor_sync(0xffffffffu, s, 4);
+      if ((lane & 7) == 0) sd[it * 4 + (lane >> 3)][2 * warp + j] = s;
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < H * 16; i += 256) {
+    const int hh = i >> 4, tl = i & 15, t = t0 + tl;
+    const long long idx = (static_cast<long long>(b) * H + hh) * Tpad + t;
+    if (t < T) {
+      delta[idx] = sd[hh][tl];
+      lse2[idx] = __ldg(lse + (static_cast<long long>(b) * H + hh) * T + t) * kLog2e;
+    } else {
+      delta[idx] = 0.f;
+      lse2[idx] = INFINITY;
+    }
+  }
+}
+
 // backward main kernel.  CTA = (128 keys, head, image) looping over the queries in sub-blocks of 64;
 // 16 compute warps (TMEM lane quadrant = warp%4 = 32 keys, column group = warp/4 = 16 queries) + 1 control
 // warp that owns TMA and MMA issue.  Per sub-block u (buffer x = u&1):
@@ -672,8 +735,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
     mbar_wait(bar_g, (nq - 1) & 1);
     tc_fence_after_sync();
     reduce_dq(nq - 1);
-    if (elect_one()) tma_store_wait_all<0>();
-    // dV (cg 0,1) and dK·scale (cg 2,3) → dqkv[b, key, 2|1, h, :]
+    // dV (cg 0,1) and dK·scale (cg 2,3) → dqkv[b, key, 2|1, h, :]  (while the last dQ reduce-adds complete)
     {
       const bool is_dv = cg < 2;
       const int c32 = (cg & 1) * 32;
@@ -696,6 +758,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
         }
       }
     }
+    if (elect_one()) tma_store_wait_all<0>();   // the slabs must outlive the bulk reads; the reduce-adds complete before exit
   }
   tc_fence_before_sync();
   __syncthreads();
@@ -832,9 +895,17 @@ extern "C" VITK_API int vitk_attn_bwd(const void* qkv, const void* o, const void
   }
   VITK_CUDA(cudaMemsetAsync(dq_acc, 0, dq_bytes, s));
   const int BT = static_cast<int>(B * T);
-  VITK_CUDA(launch_pdl(attn_delta_kernel, dim3((static_cast<int>(B) * Tpad + 7) / 8), dim3(256), 0, s,
-                       static_cast<const __nv_bfloat16*>(o), static_cast<const __nv_bfloat16*>(d_o), lse, (int)B, (int)T, Tpad,
-                       (int)H, lse2, delta));
+  {
+    const __nv_bfloat16* po = static_cast<const __nv_bfloat16*>(o);
+    const __nv_bfloat16* pdo = static_cast<const __nv_bfloat16*>(d_o);
+    const dim3 g16(static_cast<unsigned>(B * Tpad / 16)), g8((static_cast<int>(B) * Tpad + 7) / 8);
+    static const bool legacy = [] { const char* e = getenv("VITK_ATTN_DELTA_LEGACY"); return e && atoi(e) != 0; }();
+    if (H > 16 || legacy) VITK_CUDA(launch_pdl(attn_delta_kernel, g8, dim3(256), 0, s, po, pdo, lse, (int)B, (int)T, Tpad, (int)H, lse2, delta));
+    else if (H > 12) VITK_CUDA(launch_pdl(attn_delta16_kernel<4>, g16, dim3(256), 0, s, po, pdo, lse, (int)B, (int)T, Tpad, (int)H, lse2, delta));
+    else if (H > 8) VITK_CUDA(launch_pdl(attn_delta16_kernel<3>, g16, dim3(256), 0, s, po, pdo, lse, (int)B, (int)T, Tpad, (int)H, lse2, delta));
+    else if (H > 4) VITK_CUDA(launch_pdl(attn_delta16_kernel<2>, g16, dim3(256), 0, s, po, pdo, lse, (int)B, (int)T, Tpad, (int)H, lse2, delta));
+    else VITK_CUDA(launch_pdl(attn_delta16_kernel<1>, g16, dim3(256), 0, s, po, pdo, lse, (int)B, (int)T, Tpad, (int)H, lse2, delta));
+  }
   VITK_LAUNCH_CHECK("attn_delta_kernel");
   const dim3 grid(static_cast<unsigned>((T + kTile - 1) / kTile), static_cast<unsigned>(H), static_cast<unsigned>(B));
   VITK_CUDA(launch_pdl(attn_bwd_kernel, grid, dim3(kBwdThreads), kBwdSmemBytes, s, tm_qkv, tm_q64, tm_do, tm_dq,

@@ -30,7 +30,8 @@ def _ref(qkv, do, scale):
 # (300 → 3 tiles = pair + single; 385 → 4 tiles), the model's 577 (2 pairs + single, 65-key tail), 5 full tiles (640) and
 # 8 key blocks (1024: the 3-deep K/V ring is recycled)
 @pytest.mark.parametrize("B,T,H", [(1, 128, 1), (1, 64, 2), (2, 17, 2), (2, 129, 3), (2, 197, 12), (1, 256, 2), (2, 577, 12),
-                                   (1, 300, 16), (1, 385, 2), (1, 640, 2), (1, 1024, 1), (16, 577, 12)])
+                                   (1, 300, 16), (1, 385, 2), (1, 640, 2), (1, 1024, 1), (16, 577, 12),
+                                   (1, 130, 6), (1, 70, 20)])      # head counts of every attn_delta instantiation (≤4, ≤8, ≤12, ≤16, >16)
 def test_attention_fwd_bwd(ops, B, T, H):
     g = torch.Generator().manual_seed(T * 10 + H)
     qkv = (torch.randn(B, T, 3, H, 64, generator=g)).to(dev).to(bf16)
