@@ -84,6 +84,11 @@ struct Gemm2Params {
                        // (n_tiles = n_full + n_half); all full tiles come first in the work order
   int epi;
   int has_d2;
+  int l2_hints;       // VITK_L2_HINTS (default 1): the second output (GELU', saved for backward, not read again in this pass) is
+                      // stored with the L2 evict_first policy so that it does not push gelu(u) — the next GEMM's operand — out
+                      // of L2.  A/B on the step (profiles/r02_l2_hints_ab.txt): +0.5 %, at the edge of the run-to-run noise;
+                      // evict_first LOADS of the single-use multiplier / residual / LayerNorm-backward inputs changed nothing
+                      // and were removed.
   int dbg;            // VITK_GEMM_DBG experiment bits (0 in production): 1 skip stores, 2 skip aux, 4 skip TMEM loads,
                       // 8 every CTA loads tile (0,0) (operands always L2-resident), 16 no MMAs (load pipeline only),
                       // 32 no TMA loads after the first ring fill (MMA pipeline only)
@@ -396,6 +401,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     auto tile_row0 = [&](const Work2& it) { return it.m_blk * (2 * k2BM) + static_cast<int>(cta_rank) * k2BM + quad * 32; };
     auto tile_col0 = [&](const Work2& it) { return it.n0 + part * (it.bn / kParts); };   // this warp's column part of the tile
 
+    const bool d2_stream = (p.l2_hints & 1) != 0;   // (the policy is created where it is used: 2 registers the epilogue does not have to spare)
     uint4 axA[4], axB[4];  // aux chunks in flight (coalesced layout); named, never indexed dynamically, so they stay in registers
     auto load_aux = [&](uint4 (&dst)[4], int row0, int col) {
       const uint8_t* base = reinterpret_cast<const uint8_t*>(p.aux) +
@@ -423,7 +429,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       *col = tile_col0(nxt) + (c - nch) * cw;
       return true;
     };
-    auto emit = [&](const CUtensorMap* map, int col, int row0, const uint4 (&q)[4]) {
+    auto emit = [&](const CUtensorMap* map, int col, int row0, const uint4 (&q)[4], bool stream_out = false) {
       if (p.dbg & 1) return;
       // wait until the store issued `nout` stores ago has finished reading its slab, then reuse it
       if (elect_one()) { if (nout == k2Slabs) tma_store_wait_read<k2Slabs - 1>(); else tma_store_wait_read<k2Slabs - 2>(); }
@@ -435,6 +441,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       __syncwarp();
       if (elect_one()) {
         if (epi == VITK_EPI_ACCUM_F32) tma_reduce_add_2d(map, slab, col, row0);
+        else if (stream_out) tma_store_2d_hint(map, slab, col, row0, l2_policy_evict_first());
         else tma_store_2d(map, slab, col, row0);
         tma_store_commit();
       }
@@ -576,7 +583,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
               qg[j] = make_uint4(wg[0], wg[1], wg[2], wg[3]);
             }
             emit(&tma_d, col, row0, q);
-            if (p.has_d2) emit(&tma_d2, col, row0, qg);
+            if (p.has_d2) emit(&tma_d2, col, row0, qg, d2_stream);
             break;
           }
           case VITK_EPI_MUL_BF16:
@@ -842,6 +849,8 @@ int gemm2_try_launch(const vitk_gemm_args& a, cudaStream_t stream, bool* handled
   {
     static const int dbg = [] { const char* e = getenv("VITK_GEMM_DBG"); return e ? atoi(e) : 0; }();
     p.dbg = dbg;
+    static const int hints = [] { const char* e = getenv("VITK_L2_HINTS"); return e ? atoi(e) : 1; }();
+    p.l2_hints = hints;
   }
   p.aux = a.aux;
   p.ld_aux = a.ld_aux;
