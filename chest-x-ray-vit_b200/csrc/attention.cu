@@ -493,6 +493,17 @@ __global__ void __launch_bounds__(256) attn_delta16_kernel(const __nv_bfloat16* 
 // and reduced into the fp32 accumulator one block later with per-warp TMA reduce-adds.  Keys ≥ T need no
 // masking (their dV/dK rows are never stored, their dQ contribution multiplies zero-filled K rows);
 // queries ≥ T have lse = +inf in the padded statistics, hence P = dS = 0.
+// Persistent: the grid is one CTA per SM and every CTA walks work items w = blockIdx.x, + gridDim.x, … (item = key
+// block × head × image, key block fastest).  Ring / buffer indices and barrier parities run on GLOBAL counters
+// (sub-blocks g, 128-query blocks G, items), so nothing is re-initialised between items: the load warp brings the next
+// item's K/V and first Q/dO sub-tiles as soon as the previous item's last MMA has retired (bar_item), the MMA warp
+// issues the next item's first score MMAs while the compute warps still drain dQ / dV / dK of the previous one, and
+// only the first dV/dK MMA of an item waits for that drain (bar_acc).  This hides the per-CTA prologue (TMEM
+// allocation, barrier set-up, the K/V + Q/dO round trip) behind the epilogue: 123.9 → 117.5 µs per layer all-in at
+// B = 16.  (Tried on top and dropped, 119.7 µs: K/V double-buffered in shared memory with the next item's scores queued
+// right behind the last dQ MMA — the boundary was already hidden behind the compute warps' epilogue, and the variable
+// K/V descriptor offsets cost the MMA-issue warp ≈100 cycles per sub-block.)  VITK_ATTN_BWD_PERSIST=0 launches one
+// CTA per item (the same code, one trip).
 constexpr int kBwdComputeWarps = 16;
 constexpr int kBwdThreads = (kBwdComputeWarps + 2) * 32;   // 16 compute warps + MMA-issue warp + TMA-load warp
 constexpr int kQSub = 64;
@@ -503,14 +514,14 @@ constexpr int kBwdSmemDO = kBwdSmemQ + 2 * kTileBytes;   // ring of 4 sub-tiles
 constexpr int kBwdSmemDSt = kBwdSmemDO + 2 * kTileBytes; // dSᵀ [128 keys × 128 q], one tile per 128-query block parity
 constexpr int kBwdSmemDqS = kBwdSmemDSt + 4 * kTileBytes;   // per-warp dQ staging slabs: 16 × [32 q × 16 f32], 64 B swizzle
 constexpr int kBwdSmemBar = kBwdSmemDqS + kBwdComputeWarps * 2048;
-constexpr int kBwdSmemBytes = kBwdSmemBar + 128 + 1024;
+constexpr int kBwdSmemBytes = kBwdSmemBar + 256 + 1024;   // 16 barriers + the TMEM slot, + alignment slack
 // TMEM columns: buffer x: Sᵀ/Pᵀ [128x, 128x+64), dPᵀ/dSᵀ [128x+64, 128x+128); dV [256,320) dK [320,384) dQ[2] [384,512)
 constexpr int kBwdTmemCols = 512;
 
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant__ CUtensorMap tma_q64,
                 const __grid_constant__ CUtensorMap tma_do64, const __grid_constant__ CUtensorMap tma_dq, const float* __restrict__ lse2, const float* __restrict__ delta,
-                __nv_bfloat16* __restrict__ dqkv, int T, int Tpad, int H, float scale, float scale_log2, long long* tl) {
+                __nv_bfloat16* __restrict__ dqkv, int T, int Tpad, int H, int B, float scale, float scale_log2, long long* tl_arg) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sK = smem + kBwdSmemK;
@@ -524,21 +535,21 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
   uint64_t* bar_pd = bar_kv + 7;  // [2] Pᵀ_x / dSᵀ_x written by the 16 compute warps
   uint64_t* bar_g = bar_kv + 9;   // every MMA up to and including dQ of a 128-query block retired
   uint64_t* bar_free = bar_kv + 10;  // [4] dV/dK of the sub-block using this Q/dO sub-tile retired
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_kv + 14);
+  uint64_t* bar_item = bar_kv + 14;  // every MMA of a work item retired: K/V may be overwritten by the next item's
+  uint64_t* bar_acc = bar_kv + 15;   // the 16 compute warps have read dV/dK of a work item out of TMEM
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_kv + 16);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int kb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int nq = (T + kTile - 1) / kTile;
+  const int nq = (T + kTile - 1) / kTile;        // key blocks per (image, head) = 128-query blocks per work item
   const int nsub = (T + kQSub - 1) / kQSub;
-  const int colq = h * kDh, colk = (H + h) * kDh, colv = (2 * H + h) * kDh;
-  const int key0 = kb * kTile;
+  const int total_items = nq * H * B;
 
   if (tid == 0) {
     tma_prefetch_desc(&tma_qkv);
     tma_prefetch_desc(&tma_q64);
     tma_prefetch_desc(&tma_do64);
     tma_prefetch_desc(&tma_dq);
-    for (int i = 0; i < 14; ++i) mbar_init(bar_kv + i, (i == 7 || i == 8) ? kBwdComputeWarps : 1);
+    for (int i = 0; i < 16; ++i) mbar_init(bar_kv + i, (i == 7 || i == 8 || i == 15) ? kBwdComputeWarps : 1);
     fence_mbar_init();
   }
   if (warp == kBwdComputeWarps) tmem_alloc(tmem_slot, kBwdTmemCols);
@@ -567,7 +578,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
     const uint64_t q_mnmaj = umma_smem_desc(smem_u32(sQ), kQSub * 128, 1024);
     const uint64_t do_mnmaj = umma_smem_desc(smem_u32(sDO), kQSub * 128, 1024);
     const uint64_t dst_mnmaj = umma_smem_desc(smem_u32(sDSt), kTileBytes, 1024);
-    auto issue_scores = [&](int u) {
+    auto issue_scores = [&](int u) {             // u: GLOBAL sub-block index
       const int x = u & 1;
       const uint64_t boff = static_cast<uint64_t>((u & 3) * kSub16);
       mbar_wait(&bar_qd[u & 3], (u >> 2) & 1);
@@ -581,13 +592,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
         tc_commit(&bar_s[x]);
       }
     };
-    mbar_wait(bar_kv, 0);
-    issue_scores(0);
-    if (nsub > 1) issue_scores(1);
-    for (int u = 0; u < nsub; ++u) {
-      const int i = u >> 1, hq = u & 1, x = u & 1;
-      const uint64_t boff = static_cast<uint64_t>((u & 3) * kSub16);
-      mbar_wait(&bar_pd[x], (u >> 1) & 1);
+    int g = 0, G = 0, item = 0;                  // global sub-block / 128-query-block / work-item counters of this CTA
+    for (int w = blockIdx.x; w < total_items; w += gridDim.x, ++item) {
+    long long* tl = item == 0 ? tl_arg : nullptr;
+    mbar_wait(bar_kv, item & 1);
+    issue_scores(g);
+    if (nsub > 1) issue_scores(g + 1);
+    for (int u = 0; u < nsub; ++u, ++g) {
+      const int hq = u & 1, x = g & 1;
+      const uint64_t boff = static_cast<uint64_t>((g & 3) * kSub16);
+      mbar_wait(&bar_pd[x], (g >> 1) & 1);
+      if (u == 0 && item > 0) mbar_wait(bar_acc, (item - 1) & 1);   // dV/dK of the previous item have left TMEM
       VITK_STAMP(16 * u + 0);
       tc_fence_after_sync();
       const uint32_t t_p = tmem_base + x * 128, t_ds = t_p + 64;
@@ -599,42 +614,47 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
 #pragma unroll
         for (int k = 0; k < kQSub / 16; ++k)   // dK[key,d] += Σ_q dSᵀ[key,q]·Q[q,d]
           tc_mma_bf16_ts(tm_dk, t_ds + 16 * k, q_mnmaj + boff + 128 * k, idesc_km, (u > 0 || k > 0) ? 1u : 0u);
-        tc_commit(&bar_free[u & 3]);
+        tc_commit(&bar_free[g & 3]);
         if (block_done) {
 #pragma unroll
           for (int k = 0; k < kTile / 16; ++k)   // dQ[q,d] = Σ_key dS[q,key]·K[key,d]; A = dSᵀ smem tile read MN-major
-            tc_mma_bf16(tm_dq + (i & 1) * kDh, dst_mnmaj + static_cast<uint64_t>((i & 1) * 2 * kTile16) + 128 * k,
+            tc_mma_bf16(tm_dq + (G & 1) * kDh, dst_mnmaj + static_cast<uint64_t>((G & 1) * 2 * kTile16) + 128 * k,
                         k_mnmaj + 128 * k, idesc_mm, k > 0);
           tc_commit(bar_g);
+          if (u == nsub - 1) tc_commit(bar_item);
         }
       }
+      if (block_done) ++G;
       VITK_STAMP(16 * u + 1);
-      if (u + 2 < nsub) issue_scores(u + 2);   // queued right behind: MMAs retire in issue order
+      if (u + 2 < nsub) issue_scores(g + 2);   // queued right behind: MMAs retire in issue order
       VITK_STAMP(16 * u + 2);
       VITK_STAMP(16 * u + 3);
+    }
     }
     __syncwarp();
   } else if (warp == kBwdComputeWarps + 1) {
     // ------------------------------------------------------------------ load warp: K/V once, then the Q/dO ring.
     // (A separate warp: waiting here for a ring slot to be released — i.e. for dV/dK MMAs to retire — must not
     // hold up the MMA-issue warp, which would stall the whole score → softmax → dV/dK chain of the other buffer.)
-    auto load_qd = [&](int u) {              // sub-block u → ring slot u&3
-      const int slot = u & 3;
+    int g = 0, item = 0;
+    for (int w = blockIdx.x; w < total_items; w += gridDim.x, ++item) {
+      const int kb = w % nq, h = (w / nq) % H, b = w / (nq * H);
+      const int colq = h * kDh, colk = (H + h) * kDh, colv = (2 * H + h) * kDh;
+      if (item > 0) mbar_wait(bar_item, (item - 1) & 1);   // the previous item's MMAs no longer read K / V
       if (elect_one()) {
-        mbar_arrive_expect_tx(&bar_qd[slot], 2 * kQSub * 128);
-        tma_load_3d(sQ + slot * (kQSub * 128), &tma_q64, &bar_qd[slot], colq, u * kQSub, b);
-        tma_load_3d(sDO + slot * (kQSub * 128), &tma_do64, &bar_qd[slot], colq, u * kQSub, b);
+        mbar_arrive_expect_tx(bar_kv, 2 * kTileBytes);
+        tma_load_3d(sK, &tma_qkv, bar_kv, colk, kb * kTile, b);
+        tma_load_3d(sV, &tma_qkv, bar_kv, colv, kb * kTile, b);
       }
-    };
-    if (elect_one()) {
-      mbar_arrive_expect_tx(bar_kv, 2 * kTileBytes);
-      tma_load_3d(sK, &tma_qkv, bar_kv, colk, key0, b);
-      tma_load_3d(sV, &tma_qkv, bar_kv, colv, key0, b);
-    }
-    for (int u = 0; u < 4 && u < nsub; ++u) load_qd(u);
-    for (int u = 4; u < nsub; ++u) {         // slot u&3 was last used by sub-block u−4: wait until its dV/dK retired
-      mbar_wait(&bar_free[u & 3], ((u - 4) >> 2) & 1);
-      load_qd(u);
+      for (int u = 0; u < nsub; ++u, ++g) {  // sub-block g → ring slot g&3, last used by sub-block g−4: wait until its dV/dK retired
+        const int slot = g & 3;
+        if (g >= 4) mbar_wait(&bar_free[slot], ((g - 4) >> 2) & 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&bar_qd[slot], 2 * kQSub * 128);
+          tma_load_3d(sQ + slot * (kQSub * 128), &tma_q64, &bar_qd[slot], colq, u * kQSub, b);
+          tma_load_3d(sDO + slot * (kQSub * 128), &tma_do64, &bar_qd[slot], colq, u * kQSub, b);
+        }
+      }
     }
     __syncwarp();
   } else {
@@ -642,14 +662,20 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
     const int quad = warp & 3, cg = warp >> 2;
     const int key_row = quad * 32 + lane;  // TMEM lane = key (Sᵀ, dPᵀ, dV, dK) or query (dQ)
     const uint32_t lane_field = static_cast<uint32_t>(quad * 32) << 16;
-    const float* stat_lse = lse2 + (static_cast<long long>(b) * H + h) * Tpad + cg * 16;
-    const float* stat_dlt = delta + (static_cast<long long>(b) * H + h) * Tpad + cg * 16;
     // this warp's 32 query rows × 16 head-dim columns of dQ_i: TMEM → swizzled slab → one TMA reduce-add into the
     // fp32 accumulator (rows ≥ T are clipped by the tensor map)
     uint8_t* dq_slab = smem + kBwdSmemDqS + warp * 2048;
-    auto reduce_dq = [&](int i) {
+    int g = 0, item = 0;
+    for (int w = blockIdx.x; w < total_items; w += gridDim.x, ++item) {
+    long long* tl = item == 0 ? tl_arg : nullptr;
+    const int kb = w % nq, h = (w / nq) % H, b = w / (nq * H);
+    const int key0 = kb * kTile;
+    const int G0 = item * nq;                      // global index of this item's first 128-query block
+    const float* stat_lse = lse2 + (static_cast<long long>(b) * H + h) * Tpad + cg * 16;
+    const float* stat_dlt = delta + (static_cast<long long>(b) * H + h) * Tpad + cg * 16;
+    auto reduce_dq = [&](int i) {                  // i: block index within the item; TMEM buffer / barrier parity by G0 + i
       uint32_t r[16];
-      tmem_ld_32x16(tm_dq + (i & 1) * kDh + lane_field + cg * 16, r);
+      tmem_ld_32x16(tm_dq + ((G0 + i) & 1) * kDh + lane_field + cg * 16, r);
       if (elect_one()) tma_store_wait_read<0>();   // previous block's reduce has finished reading the slab
       __syncwarp();
       tmem_ld_wait();
@@ -671,10 +697,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
       l4[y] = __ldg(reinterpret_cast<const float4*>(stat_lse) + y);
       d4[y] = __ldg(reinterpret_cast<const float4*>(stat_dlt) + y);
     }
-    for (int u = 0; u < nsub; ++u) {
-      const int i = u >> 1, hq = u & 1, x = u & 1;
+    for (int u = 0; u < nsub; ++u, ++g) {
+      const int i = u >> 1, hq = u & 1, x = g & 1;
       if (warp == 0) VITK_STAMP(16 * u + 8);
-      mbar_wait(&bar_s[x], (u >> 1) & 1);
+      mbar_wait(&bar_s[x], (g >> 1) & 1);
       if (warp == 0) VITK_STAMP(16 * u + 9);
       tc_fence_after_sync();
       const uint32_t t_s = tmem_base + x * 128 + lane_field + cg * 16, t_dp = t_s + 64;
@@ -710,7 +736,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
       tmem_st_32x8(t_dp, dk);       // dSᵀ → this warp's own dPᵀ columns: A operand of dK
       {                             // dSᵀ → smem tile [128 keys × 128 q] (two 64-query halves), A operand of dQ
         // (double-buffered by block parity: dQ of block i may still be pending when block i+1's first half is written)
-        uint8_t* rowp = sDSt + (i & 1) * 2 * kTileBytes + hq * kTileBytes + key_row * 128;
+        uint8_t* rowp = sDSt + ((G0 + i) & 1) * 2 * kTileBytes + hq * kTileBytes + key_row * 128;
         *reinterpret_cast<uint4*>(rowp + (((2 * cg) ^ (key_row & 7)) << 4)) = make_uint4(dk[0], dk[1], dk[2], dk[3]);
         *reinterpret_cast<uint4*>(rowp + (((2 * cg + 1) ^ (key_row & 7)) << 4)) = make_uint4(dk[4], dk[5], dk[6], dk[7]);
       }
@@ -721,18 +747,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
       if (warp == 0) VITK_STAMP(16 * u + 12);
       if (lane == 0) mbar_arrive(&bar_pd[x]);
       if (hq == 1 && i > 0) {       // dQ of the previous 128-query block: its MMAs were issued two sub-blocks ago
-        mbar_wait(bar_g, (i - 1) & 1);
+        mbar_wait(bar_g, (G0 + i - 1) & 1);
         tc_fence_after_sync();
         reduce_dq(i - 1);
       }
       if (warp == 0) VITK_STAMP(16 * u + 13);
     }
     if (nq > 1 && (nsub & 1)) {     // an odd tail sub-block skipped the hq == 1 step that drains block nq−2
-      mbar_wait(bar_g, (nq - 2) & 1);
+      mbar_wait(bar_g, (G0 + nq - 2) & 1);
       tc_fence_after_sync();
       reduce_dq(nq - 2);
     }
-    mbar_wait(bar_g, (nq - 1) & 1);
+    mbar_wait(bar_g, (G0 + nq - 1) & 1);
     tc_fence_after_sync();
     reduce_dq(nq - 1);
     // dV (cg 0,1) and dK·scale (cg 2,3) → dqkv[b, key, 2|1, h, :]  (while the last dQ reduce-adds complete)
@@ -742,6 +768,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
       uint32_t r[32];
       tmem_ld_32x32((is_dv ? tm_dv : tm_dk) + lane_field + c32, r);
       tmem_ld_wait();
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_acc);      // the next item's dV / dK MMAs may overwrite the accumulators
       const float mul = is_dv ? 1.0f : scale;
       const int key = key0 + key_row;
       if (key < T) {
@@ -758,6 +787,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
         }
       }
     }
+    }   // work items
     if (elect_one()) tma_store_wait_all<0>();   // the slabs must outlive the bulk reads; the reduce-adds complete before exit
   }
   tc_fence_before_sync();
@@ -907,10 +937,13 @@ extern "C" VITK_API int vitk_attn_bwd(const void* qkv, const void* o, const void
     else VITK_CUDA(launch_pdl(attn_delta16_kernel<1>, g16, dim3(256), 0, s, po, pdo, lse, (int)B, (int)T, Tpad, (int)H, lse2, delta));
   }
   VITK_LAUNCH_CHECK("attn_delta_kernel");
-  const dim3 grid(static_cast<unsigned>((T + kTile - 1) / kTile), static_cast<unsigned>(H), static_cast<unsigned>(B));
-  VITK_CUDA(launch_pdl(attn_bwd_kernel, grid, dim3(kBwdThreads), kBwdSmemBytes, s, tm_qkv, tm_q64, tm_do, tm_dq,
+  const long long items = ((T + kTile - 1) / kTile) * H * B;
+  VITK_REQUIRE(items < (1ll << 30), VITK_EINVAL, "attn_bwd: too many (key block, head, image) work items");
+  static const bool persist = [] { const char* e = getenv("VITK_ATTN_BWD_PERSIST"); return !e || atoi(e) != 0; }();
+  const long long ctas = persist && items > num_sms() ? num_sms() : items;
+  VITK_CUDA(launch_pdl(attn_bwd_kernel, dim3(static_cast<unsigned>(ctas)), dim3(kBwdThreads), kBwdSmemBytes, s, tm_qkv, tm_q64, tm_do, tm_dq,
                        static_cast<const float*>(lse2), static_cast<const float*>(delta), static_cast<__nv_bfloat16*>(dqkv), (int)T, Tpad,
-                       (int)H, scale, scale * kLog2e, g_timeline));
+                       (int)H, (int)B, scale, scale * kLog2e, g_timeline));
   VITK_LAUNCH_CHECK("attn_bwd_kernel");
   const long long n8 = static_cast<long long>(BT) * H * kDh / 8;
   VITK_CUDA(launch_pdl(attn_dq_store_kernel, dim3(static_cast<unsigned>((n8 + 255) / 256)), dim3(256), 0, s,
