@@ -493,8 +493,12 @@ __global__ void __launch_bounds__(256) attn_delta16_kernel(const __nv_bfloat16* 
 // and reduced into the fp32 accumulator one block later with per-warp TMA reduce-adds.  Keys ≥ T need no
 // masking (their dV/dK rows are never stored, their dQ contribution multiplies zero-filled K rows);
 // queries ≥ T have lse = +inf in the padded statistics, hence P = dS = 0.
-// Persistent: the grid is one CTA per SM and every CTA walks work items w = blockIdx.x, + gridDim.x, … (item = key
-// block × head × image, key block fastest).  Ring / buffer indices and barrier parities run on GLOBAL counters
+// Persistent: the grid is one CTA per SM and every CTA walks work items (item = key block × head × image, key block
+// fastest): first w = blockIdx.x, then whatever a global atomic counter hands out (gridDim.x, gridDim.x + 1, …) — the
+// load warp draws the next item while the current one runs and publishes it to the other warps through shared memory
+// (item_ring / bar_id).  A draw instead of a fixed stride because a CTA that starts late (its SM still held by a
+// communication kernel of the gradient all-reduce) must not sit on a full share of the work.
+// Ring / buffer indices and barrier parities run on GLOBAL counters
 // (sub-blocks g, 128-query blocks G, items), so nothing is re-initialised between items: the load warp brings the next
 // item's K/V and first Q/dO sub-tiles as soon as the previous item's last MMA has retired (bar_item), the MMA warp
 // issues the next item's first score MMAs while the compute warps still drain dQ / dV / dK of the previous one, and
@@ -521,7 +525,7 @@ constexpr int kBwdTmemCols = 512;
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant__ CUtensorMap tma_q64,
                 const __grid_constant__ CUtensorMap tma_do64, const __grid_constant__ CUtensorMap tma_dq, const float* __restrict__ lse2, const float* __restrict__ delta,
-                __nv_bfloat16* __restrict__ dqkv, int T, int Tpad, int H, int B, float scale, float scale_log2, long long* tl_arg) {
+                __nv_bfloat16* __restrict__ dqkv, int T, int Tpad, int H, int B, float scale, float scale_log2, int* __restrict__ work_counter, long long* tl_arg) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sK = smem + kBwdSmemK;
@@ -537,7 +541,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
   uint64_t* bar_free = bar_kv + 10;  // [4] dV/dK of the sub-block using this Q/dO sub-tile retired
   uint64_t* bar_item = bar_kv + 14;  // every MMA of a work item retired: K/V may be overwritten by the next item's
   uint64_t* bar_acc = bar_kv + 15;   // the 16 compute warps have read dV/dK of a work item out of TMEM
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_kv + 16);
+  uint64_t* bar_id = bar_kv + 16;    // [2] the id of work item n (slot n & 1) has been published in item_ring
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_kv + 18);
+  volatile int* item_ring = reinterpret_cast<volatile int*>(bar_kv + 18) + 1;   // [2] global work-item index, −1 = no more work
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nq = (T + kTile - 1) / kTile;        // key blocks per (image, head) = 128-query blocks per work item
@@ -549,7 +555,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
     tma_prefetch_desc(&tma_q64);
     tma_prefetch_desc(&tma_do64);
     tma_prefetch_desc(&tma_dq);
-    for (int i = 0; i < 16; ++i) mbar_init(bar_kv + i, (i == 7 || i == 8 || i == 15) ? kBwdComputeWarps : 1);
+    for (int i = 0; i < 18; ++i) mbar_init(bar_kv + i, (i == 7 || i == 8 || i == 15) ? kBwdComputeWarps : 1);
     fence_mbar_init();
   }
   if (warp == kBwdComputeWarps) tmem_alloc(tmem_slot, kBwdTmemCols);
@@ -593,7 +599,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
       }
     };
     int g = 0, G = 0, item = 0;                  // global sub-block / 128-query-block / work-item counters of this CTA
-    for (int w = blockIdx.x; w < total_items; w += gridDim.x, ++item) {
+    for (int w = blockIdx.x; w >= 0; ++item) {
     long long* tl = item == 0 ? tl_arg : nullptr;
     mbar_wait(bar_kv, item & 1);
     issue_scores(g);
@@ -630,6 +636,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
       VITK_STAMP(16 * u + 2);
       VITK_STAMP(16 * u + 3);
     }
+    mbar_wait(&bar_id[(item + 1) & 1], (item >> 1) & 1);            // the load warp drew the next item long ago (item n is the
+                                                                    // ⌊(n−1)/2⌋-th publication on slot n & 1: item 0 is never published)
+    w = item_ring[(item + 1) & 1];
     }
     __syncwarp();
   } else if (warp == kBwdComputeWarps + 1) {
@@ -637,7 +646,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
     // (A separate warp: waiting here for a ring slot to be released — i.e. for dV/dK MMAs to retire — must not
     // hold up the MMA-issue warp, which would stall the whole score → softmax → dV/dK chain of the other buffer.)
     int g = 0, item = 0;
-    for (int w = blockIdx.x; w < total_items; w += gridDim.x, ++item) {
+    int drawn = 0;                                         // lane 0: the draw in flight (the index of item + 1)
+    if (lane == 0) drawn = static_cast<int>(gridDim.x) + atomicAdd(work_counter, 1);
+    for (int w = blockIdx.x; w >= 0; ++item) {
       const int kb = w % nq, h = (w / nq) % H, b = w / (nq * H);
       const int colq = h * kDh, colk = (H + h) * kDh, colv = (2 * H + h) * kDh;
       if (item > 0) mbar_wait(bar_item, (item - 1) & 1);   // the previous item's MMAs no longer read K / V
@@ -645,6 +656,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
         mbar_arrive_expect_tx(bar_kv, 2 * kTileBytes);
         tma_load_3d(sK, &tma_qkv, bar_kv, colk, kb * kTile, b);
         tma_load_3d(sV, &tma_qkv, bar_kv, colv, kb * kTile, b);
+      }
+      // publish item + 1 (drawn a whole item ago, so the atomic's round trip — behind the bulk reduce-adds in L2 — is
+      // never waited for) and draw item + 2.  Every warp has started item − 1 by now (its MMAs have retired), so slot
+      // (item + 1) & 1, last read when item − 1 began, is free.
+      int nxt = __shfl_sync(0xffffffffu, drawn, 0);
+      nxt = nxt < total_items ? nxt : -1;
+      if (lane == 0) {
+        item_ring[(item + 1) & 1] = nxt;
+        mbar_arrive(&bar_id[(item + 1) & 1]);              // (release: the store above is visible to whoever passes the wait)
+        if (nxt >= 0) drawn = static_cast<int>(gridDim.x) + atomicAdd(work_counter, 1);
       }
       for (int u = 0; u < nsub; ++u, ++g) {  // sub-block g → ring slot g&3, last used by sub-block g−4: wait until its dV/dK retired
         const int slot = g & 3;
@@ -655,6 +676,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
           tma_load_3d(sDO + slot * (kQSub * 128), &tma_do64, &bar_qd[slot], colq, u * kQSub, b);
         }
       }
+      w = nxt;
     }
     __syncwarp();
   } else {
@@ -666,7 +688,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
     // fp32 accumulator (rows ≥ T are clipped by the tensor map)
     uint8_t* dq_slab = smem + kBwdSmemDqS + warp * 2048;
     int g = 0, item = 0;
-    for (int w = blockIdx.x; w < total_items; w += gridDim.x, ++item) {
+    for (int w = blockIdx.x; w >= 0; ++item) {
     long long* tl = item == 0 ? tl_arg : nullptr;
     const int kb = w % nq, h = (w / nq) % H, b = w / (nq * H);
     const int key0 = kb * kTile;
@@ -787,6 +809,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
         }
       }
     }
+    mbar_wait(&bar_id[(item + 1) & 1], (item >> 1) & 1);
+    w = item_ring[(item + 1) & 1];
     }   // work items
     if (elect_one()) tma_store_wait_all<0>();   // the slabs must outlive the bulk reads; the reduce-adds complete before exit
   }
@@ -890,9 +914,10 @@ static size_t bwd_stats_bytes(int64_t B, int64_t T, int64_t H) {
 static size_t bwd_dq_bytes(int64_t B, int64_t T, int64_t H) {
   return (static_cast<size_t>(B) * T * H * kDh * sizeof(float) + 255) / 256 * 256;
 }
-// workspace = fp32 dQ accumulator [B,T,H,64] | lse·log2e [B,H,Tpad] | Δ [B,H,Tpad]
+// workspace = fp32 dQ accumulator [B,T,H,64] | work-item counter (256 B, cleared with the accumulator) | lse·log2e [B,H,Tpad] | Δ [B,H,Tpad]
+constexpr size_t kBwdCounterBytes = 256;
 extern "C" VITK_API size_t vitk_attn_bwd_workspace_bytes(int64_t B, int64_t T, int64_t H) {
-  return bwd_dq_bytes(B, T, H) + 2 * bwd_stats_bytes(B, T, H);
+  return bwd_dq_bytes(B, T, H) + kBwdCounterBytes + 2 * bwd_stats_bytes(B, T, H);
 }
 
 extern "C" VITK_API int vitk_attn_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, int64_t B, int64_t T,
@@ -906,8 +931,9 @@ extern "C" VITK_API int vitk_attn_bwd(const void* qkv, const void* o, const void
   const size_t dq_bytes = bwd_dq_bytes(B, T, H);
   const int Tpad = static_cast<int>((T + kTile - 1) / kTile * kTile);
   float* dq_acc = static_cast<float*>(workspace);
-  float* lse2 = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + dq_bytes);
-  float* delta = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + dq_bytes + bwd_stats_bytes(B, T, H));
+  int* work_counter = reinterpret_cast<int*>(static_cast<uint8_t*>(workspace) + dq_bytes);
+  float* lse2 = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + dq_bytes + kBwdCounterBytes);
+  float* delta = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + dq_bytes + kBwdCounterBytes + bwd_stats_bytes(B, T, H));
   CUtensorMap tm_qkv, tm_q64, tm_do, tm_dq;
   if (int rc = qkv_tensor_map(&tm_qkv, qkv, B, T, 3 * H * kDh)) return rc;
   if (int rc = qkv_tensor_map(&tm_q64, qkv, B, T, 3 * H * kDh, kQSub)) return rc;
@@ -923,7 +949,7 @@ extern "C" VITK_API int vitk_attn_bwd(const void* qkv, const void* o, const void
     VITK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmemBytes));
     attr_done.store(1);
   }
-  VITK_CUDA(cudaMemsetAsync(dq_acc, 0, dq_bytes, s));
+  VITK_CUDA(cudaMemsetAsync(dq_acc, 0, dq_bytes + kBwdCounterBytes, s));
   const int BT = static_cast<int>(B * T);
   {
     const __nv_bfloat16* po = static_cast<const __nv_bfloat16*>(o);
@@ -943,7 +969,7 @@ extern "C" VITK_API int vitk_attn_bwd(const void* qkv, const void* o, const void
   const long long ctas = persist && items > num_sms() ? num_sms() : items;
   VITK_CUDA(launch_pdl(attn_bwd_kernel, dim3(static_cast<unsigned>(ctas)), dim3(kBwdThreads), kBwdSmemBytes, s, tm_qkv, tm_q64, tm_do, tm_dq,
                        static_cast<const float*>(lse2), static_cast<const float*>(delta), static_cast<__nv_bfloat16*>(dqkv), (int)T, Tpad,
-                       (int)H, (int)B, scale, scale * kLog2e, g_timeline));
+                       (int)H, (int)B, scale, scale * kLog2e, work_counter, g_timeline));
   VITK_LAUNCH_CHECK("attn_bwd_kernel");
   const long long n8 = static_cast<long long>(BT) * H * kDh / 8;
   VITK_CUDA(launch_pdl(attn_dq_store_kernel, dim3(static_cast<unsigned>((n8 + 255) / 256)), dim3(256), 0, s,

@@ -1,6 +1,7 @@
 #!/bin/bash
+# quick re-validation after a kernel change: whole GPU test-suite, smoke, default bench
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_attention.py tests/test_gpu_model.py -q -m gpu --timeout 600 2>&1 | grep -E "passed|failed|^E " | tail -5
-python bench.py --steps 20 --warmup 5 --no-cpu-baseline --sustained-seconds 0 2>/dev/null | cut -c1-200
-python tools/profile_step.py > gpurun_out/plain.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/launches.csv python tools/profile_step.py > gpurun_out/ncu_launches.log 2>&1; echo "launch list rc=$?"; grep -E "attn_cls" gpurun_out/launches.csv | cut -d, -f5,15- | head -4
+O=gpurun_out
+timeout 900 python -m pytest tests -q -m gpu -x --timeout 600 > $O/pytest_gpu_all.log 2>&1; echo "pytest -m gpu rc=$?"; tail -3 $O/pytest_gpu_all.log | head -2
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1; echo "smoke rc=$?"; tail -1 $O/smoke.log
+timeout 400 python bench.py > $O/bench.json 2> $O/bench.err; echo "bench rc=$?"; cut -c1-200 $O/bench.json

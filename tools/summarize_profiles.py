@@ -21,7 +21,7 @@ with open(os.path.join(P, f"{tag}_launches.csv"), "w") as f:
     for r in rows:
         v = float(r["Metric Value"].replace(",", ""))
         v = v / 1e3 if r["Metric Unit"] == "ns" else (v * 1e3 if r["Metric Unit"] == "ms" else v)
-        name = r["Kernel Name"].split("(")[0].replace("void ", "").replace("vitk::", "")
+        name = r["Kernel Name"].replace("(int)", "").split("(")[0].replace("void ", "").replace("vitk::", "")
         f.write(f'{r["ID"]},{name},"{r["Grid Size"]}","{r["Block Size"]}",{v:.2f}\n')
         a = agg.setdefault(name, [0, 0.0])
         a[0] += 1
@@ -52,7 +52,7 @@ with open(os.path.join(P, f"{tag}_ncu_full_summary.csv"), "w") as out:
             continue
         hdr, units = r[0], r[1]
         for row in r[2:]:
-            name = row[hdr.index("Kernel Name")].split("(")[0].replace("void ", "").replace("vitk::", "")
+            name = row[hdr.index("Kernel Name")].replace("(int)", "").split("(")[0].replace("void ", "").replace("vitk::", "")
             vals = []
             for k in KEYS:
                 if k in hdr:
