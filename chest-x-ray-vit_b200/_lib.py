@@ -44,6 +44,7 @@ _PROTOS = {
     "vitk_last_error": (C.c_char_p, []),
     "vitk_patchify_u8": (C.c_int, [_p, _i64, _i64, _i64, _i64, C.POINTER(C.c_float), C.POINTER(C.c_float), _p, _p]),
     "vitk_patchify_f32": (C.c_int, [_p, _i64, _i64, _i64, _i64, _p, _p]),
+    "vitk_hflip_u8": (C.c_int, [_p, _p, _i64, _i64, _i64, _p]),
     "vitk_layernorm_fwd": (C.c_int, [_p, _i64, _p, _p, _f, _i64, _i64, _p, _p, _p, _p]),
     "vitk_layernorm_fwd_rows": (C.c_int, [_p, _i64, _p, _p, _f, _i64, _i64, _i64, _p, _p, _p, _p]),
     "vitk_layernorm_bwd": (C.c_int, [_p, _p, _i64, _p, _p, _p, _p, _i64, _i64, _p, _p, _p, _p, _p]),

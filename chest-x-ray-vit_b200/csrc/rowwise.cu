@@ -88,6 +88,31 @@ __global__ void __launch_bounds__(256) patchify_f32_kernel(const float* __restri
   o[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
 }
 
+// ------------------------------------------------------------------------- horizontal flip (training augmentation)
+// thread = one pair of mirrored 16-byte chunks of a row (or the middle chunk when W/16 is odd): load both, reverse the
+// bytes of each, store them swapped.  Images whose mask byte is 0 are skipped by whole blocks (blockIdx.y = image).
+__device__ __forceinline__ uint4 reverse16(uint4 v) {
+  return make_uint4(__byte_perm(v.w, 0, 0x0123), __byte_perm(v.z, 0, 0x0123), __byte_perm(v.y, 0, 0x0123), __byte_perm(v.x, 0, 0x0123));
+}
+__global__ void __launch_bounds__(256) hflip_u8_kernel(uint8_t* __restrict__ gray, const uint8_t* __restrict__ mask, int H, int W) {
+  const int b = blockIdx.y;
+  if (mask[b] == 0) return;
+  const int n = W / 16, pairs = (n + 1) / 2;                 // chunks per row; (left, right) pairs incl. a self-paired middle chunk
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long long>(H) * pairs) return;
+  const int row = static_cast<int>(idx / pairs), c = static_cast<int>(idx - static_cast<long long>(row) * pairs);
+  uint4* r = reinterpret_cast<uint4*>(gray + (static_cast<long long>(b) * H + row) * W);
+  const int m = n - 1 - c;
+  const uint4 left = r[c];
+  if (m == c) {
+    r[c] = reverse16(left);
+  } else {
+    const uint4 right = r[m];
+    r[c] = reverse16(right);
+    r[m] = reverse16(left);
+  }
+}
+
 // ------------------------------------------------------------------------- LayerNorm
 // One warp per row; lane owns float4 chunks lane, lane+32, ... (VPL of them; D = 128·VPL).
 template <int VPL>
@@ -387,6 +412,17 @@ extern "C" VITK_API int vitk_patchify_u8(const uint8_t* gray, int64_t B, int64_t
   patchify_u8_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       gray, static_cast<int>(B), static_cast<int>(H), static_cast<int>(W), nc, static_cast<__nv_bfloat16*>(out));
   VITK_LAUNCH_CHECK("patchify_u8_kernel");
+  return 0;
+}
+
+extern "C" VITK_API int vitk_hflip_u8(uint8_t* gray, const uint8_t* mask, int64_t B, int64_t H, int64_t W, vitk_stream_t stream) {
+  VITK_REQUIRE(gray && mask, VITK_EINVAL, "hflip_u8: NULL argument");
+  VITK_REQUIRE(B > 0 && B < 65536 && H > 0 && W > 0 && W % 16 == 0 && H < (1 << 20) && W < (1 << 20), VITK_EINVAL, "hflip_u8: bad image shape (W must be a multiple of 16)");
+  VITK_REQUIRE(aligned16(gray), VITK_EALIGN, "hflip_u8: the image buffer must be 16-byte aligned");
+  const long long per_image = H * ((W / 16 + 1) / 2);
+  hflip_u8_kernel<<<dim3(static_cast<unsigned>((per_image + 255) / 256), static_cast<unsigned>(B)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      gray, mask, static_cast<int>(H), static_cast<int>(W));
+  VITK_LAUNCH_CHECK("hflip_u8_kernel");
   return 0;
 }
 

@@ -11,7 +11,11 @@ on the GPU) and yields batches already resident in HBM:
   * and handed over with a stream-ordered event (no host synchronisation); a slot is reused only after the compute
     stream has finished with it.
 
-Nothing here touches pixel values: normalisation / im2col happen in ``vitk_patchify_u8`` / ``vitk_patchify_f32``.
+Normalisation / im2col happen in ``vitk_patchify_u8`` / ``vitk_patchify_f32``.  The one pixel operation offered here is
+the training transform's ``RandomHorizontalFlip`` (ViT-Training.py:61) for uint8 batches: ``hflip_p > 0`` draws a
+per-image mask on the host (``generator`` makes it reproducible), copies it with the batch and mirrors the selected
+images in place on the copy stream (``vitk_hflip_u8``) — a byte permutation, identical to flipping before
+ToTensor+Normalize.  ``RandomResizedCrop`` (PIL's antialiased resampling) stays with the host loader.
 """
 from __future__ import annotations
 
@@ -21,9 +25,16 @@ import torch
 
 
 class DeviceFeeder:
-    def __init__(self, batches: Iterable[Dict[str, torch.Tensor]], device: Optional[torch.device] = None, depth: int = 2):
+    def __init__(self, batches: Iterable[Dict[str, torch.Tensor]], device: Optional[torch.device] = None, depth: int = 2,
+                 hflip_p: float = 0.0, generator: Optional[torch.Generator] = None, image_key: str = "pixel_values"):
         if depth < 2:
             raise ValueError("DeviceFeeder: depth must be >= 2 (one slot in use, one in flight)")
+        if not 0.0 <= hflip_p <= 1.0:
+            raise ValueError("DeviceFeeder: hflip_p must be a probability")
+        self.hflip_p, self.generator, self.image_key = float(hflip_p), generator, image_key
+        self._mask_host: List[Optional[torch.Tensor]] = [None] * depth
+        self._mask_dev: List[Optional[torch.Tensor]] = [None] * depth
+        self.last_masks: List[Optional[torch.Tensor]] = [None] * depth      # host copy of each slot's latest flip mask
         self.batches = batches
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.depth = depth
@@ -71,8 +82,28 @@ class DeviceFeeder:
                 d.copy_(t, non_blocking=True)
                 self.h2d_bytes += t.numel() * t.element_size()
                 new_dev[k] = d
+                if self.hflip_p > 0.0 and k == self.image_key:
+                    self._flip(slot, d)
             self._ready[slot].record(self.copy_stream)
         self._slots[slot], self._pinned[slot] = new_dev, new_pin
+
+    def _flip(self, slot: int, images: torch.Tensor) -> None:
+        """RandomHorizontalFlip of the slot's uint8 batch on the copy stream (called under it, after the batch's copy)."""
+        if images.dtype != torch.uint8 or images.dim() != 3:
+            raise ValueError("DeviceFeeder: hflip_p needs uint8 grayscale batches [B,H,W] (the fp32 collate output is "
+                             "already normalised and replicated; flip it in the loader)")
+        from . import ops
+        B = images.shape[0]
+        if self._mask_host[slot] is None or self._mask_host[slot].numel() != B:
+            self._mask_host[slot] = torch.empty(B, dtype=torch.uint8, pin_memory=True)
+            self._mask_dev[slot] = torch.empty(B, dtype=torch.uint8, device=self.device)
+        self._ready[slot].synchronize()                 # the previous copy out of this pinned mask has completed
+        mask = (torch.rand(B, generator=self.generator) < self.hflip_p).to(torch.uint8)
+        self._mask_host[slot].copy_(mask)
+        self.last_masks[slot] = mask
+        self._mask_dev[slot].copy_(self._mask_host[slot], non_blocking=True)
+        self.h2d_bytes += B
+        ops.hflip_u8(images, self._mask_dev[slot])
 
     def __iter__(self) -> Iterator[Dict[str, torch.Tensor]]:
         it = iter(self.batches)

@@ -62,6 +62,16 @@ def patchify_u8(gray: torch.Tensor, mean=(0.5, 0.5, 0.5), std=(0.5, 0.5, 0.5), o
     return out
 
 
+def hflip_u8(gray: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+    """RandomHorizontalFlip on the device (ViT-Training.py:61): uint8 gray [B,H,W] mirrored IN PLACE along W where the
+    uint8 / bool mask [B] is non-zero.  Returns ``gray``."""
+    assert gray.dtype == torch.uint8 and gray.is_cuda and gray.is_contiguous() and gray.dim() == 3
+    assert mask.is_cuda and mask.is_contiguous() and mask.numel() == gray.shape[0] and mask.dtype in (torch.uint8, torch.bool)
+    B, H, W = gray.shape
+    _lib.check(_lib.lib().vitk_hflip_u8(gray.data_ptr(), mask.data_ptr(), B, H, W, _stream()), "hflip_u8")
+    return gray
+
+
 def patchify_f32(pix: torch.Tensor, out: Optional[torch.Tensor] = None):
     """fp32 NCHW [B,3,H,W] → bf16 im2col [B·P, 768] (collate_fn contract, ViT-Training.py:77-80)."""
     assert pix.dtype == f32 and pix.is_cuda and pix.is_contiguous() and pix.dim() == 4 and pix.shape[1] == 3

@@ -55,6 +55,11 @@ VITK_API int vitk_patchify_u8(const uint8_t* gray, int64_t B, int64_t H, int64_t
 VITK_API int vitk_patchify_f32(const float* pixel_values, int64_t B, int64_t H, int64_t W, int64_t patch,
                       void* out_bf16, vitk_stream_t stream);
 
+/* RandomHorizontalFlip of the training transform (ViT-Training.py:61), on the device: image b of gray u8 [B,H,W] is
+ * mirrored in place along W iff mask[b] != 0 (the caller draws the mask, p = 0.5 in torchvision).  A pure permutation of
+ * bytes: identical to flipping before ToTensor+Normalize.  W % 16 == 0. */
+VITK_API int vitk_hflip_u8(uint8_t* gray, const uint8_t* mask, int64_t B, int64_t H, int64_t W, vitk_stream_t stream);
+
 /* ------------------------------------------------------------------ LayerNorm
  * Replaces aten::native_layer_norm / native_layer_norm_backward (HF:325-326,333,340,455).
  * x fp32 [M,D] (row stride ldx elements) → y bf16 [M,D]; mean/rstd fp32 [M] saved for backward. */

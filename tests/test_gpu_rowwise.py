@@ -159,3 +159,44 @@ def test_adamw_tick_device_step_counter(ops):
         assert torch.allclose(bc.cpu(), torch.tensor([1 - 0.9 ** t, (1 - 0.999 ** t) ** -0.5]), rtol=1e-5)
     ops.adamw_tick(step, False, 0.9, 0.999, bc)
     assert step.item() == 3
+
+
+@pytest.mark.parametrize("B,H,W", [(5, 384, 384), (3, 224, 224), (2, 48, 48), (4, 16, 16), (2, 32, 80)])
+def test_hflip_u8_is_the_mirror(ops, B, H, W):
+    """RandomHorizontalFlip on the device: masked images are mirrored along W (even and odd numbers of 16-byte chunks per
+    row), the others untouched — bit for bit what torch.flip / PIL's FLIP_LEFT_RIGHT gives before ToTensor+Normalize."""
+    g = torch.Generator().manual_seed(B * 100 + W)
+    x8 = torch.randint(0, 256, (B, H, W), dtype=torch.uint8, generator=g)
+    mask = (torch.arange(B) % 2 == 0).to(torch.uint8)
+    ref = torch.where(mask.bool()[:, None, None], torch.flip(x8, dims=[-1]), x8)
+    d = x8.to(dev)
+    out = ops.hflip_u8(d, mask.to(dev))
+    assert out.data_ptr() == d.data_ptr() and torch.equal(d.cpu(), ref)
+    ops.hflip_u8(d, torch.ones(B, dtype=torch.bool, device=dev))          # all images, bool mask
+    assert torch.equal(d.cpu(), torch.flip(ref, dims=[-1]))
+    norm = ((0.5, 0.5, 0.5), (0.5, 0.5, 0.5))
+    if H % 16 == 0:
+        got = ops.patchify_u8(d, *norm)                                   # flip, then the usual transform = the reference's order
+        want = O.im2col(O.normalize_gray(torch.flip(ref, dims=[-1]), *norm), 16).reshape(-1, 768).to(torch.bfloat16)
+        assert torch.equal(got.cpu().view(torch.int16), want.view(torch.int16))
+
+
+def test_device_feeder_random_hflip(ops):
+    """DeviceFeeder(hflip_p=…): per-image masks from a seeded generator, applied on the copy stream; the fed batches are
+    the host batches mirrored where the mask says so, labels untouched."""
+    import chest_x_ray_vit_b200 as pkg
+    g = torch.Generator().manual_seed(3)
+    batches = [{"pixel_values": torch.randint(0, 256, (6, 64, 64), dtype=torch.uint8, generator=g),
+                "labels": torch.rand(6, 14, generator=g)} for _ in range(5)]
+    feeder = pkg.data.DeviceFeeder(batches, device=dev, hflip_p=0.5, generator=torch.Generator().manual_seed(11))
+    ref_gen = torch.Generator().manual_seed(11)
+    flipped = 0
+    for host, fed in zip(batches, feeder):
+        mask = torch.rand(6, generator=ref_gen) < 0.5
+        want = torch.where(mask[:, None, None], torch.flip(host["pixel_values"], dims=[-1]), host["pixel_values"])
+        torch.cuda.current_stream().synchronize()
+        assert torch.equal(fed["pixel_values"].cpu(), want) and torch.equal(fed["labels"].cpu(), host["labels"])
+        flipped += int(mask.sum())
+    assert 0 < flipped < 30
+    with pytest.raises(ValueError, match="uint8"):
+        next(iter(pkg.data.DeviceFeeder([{"pixel_values": torch.zeros(2, 3, 32, 32)}], device=dev, hflip_p=0.5)))
