@@ -11,9 +11,9 @@
 //
 // forward  : CTA = (128 queries, head, image), 4 softmax warps (thread = query row = TMEM lane) + a control warp; four
 //            CTAs per SM (128 TMEM columns each) so one CTA's softmax overlaps the others' MMAs.
-// backward : CTA = (128 keys, head, image) loops over query blocks; Sᵀ and dPᵀ live in TMEM
-//            (lane = key), dV/dK accumulate in TMEM across the loop, dQ partials are reduced
-//            into an fp32 workspace with red.global.add.
+// backward : persistent CTAs (one per SM) draw (128 keys, head, image) work items and loop over the query blocks of each;
+//            Sᵀ and dPᵀ live in TMEM (lane = key), dV/dK accumulate in TMEM across the loop, dQ partials are reduced
+//            into an fp32 workspace with TMA reduce-adds.
 #include <cuda.h>
 #include <math.h>
 

@@ -15,7 +15,8 @@
 //   test it wraps each of them in an elect/broadcast/retry loop and the MMA-issue warp, not the tensor
 //   pipe, paces the main loop: 670 instead of ≈500 cycles per K block)
 //   (epilogue warp w may only touch TMEM lanes 32·(w%4)…: quadrant = warp id % 4)
-//   warps 2..9    epilogue: TMEM → registers (one row per thread) → fused math → [32 rows × 64 B] slab in
+//   warps 2..9    (2..17 in the 16-epilogue-warp instantiation used for fc1 + GELU, template parameter EW)
+//                 epilogue: TMEM → registers (one row per thread) → fused math → [32 rows × 64 B] slab in
 //                 swizzled smem → TMA store (TMA reduce-add for split-K wgrad); outputs cross smem exactly
 //                 twice; residual / multiplier tiles are read two chunks ahead with coalesced loads and
 //                 transposed through a spare slab.
@@ -23,8 +24,9 @@
 //                 of tile i+1.
 //   schedule      static round-robin over the pairs; a 256-wide launch may mix 256- and 128-column tiles
 //                 (n_full / n_half per 256-row band, full tiles first) so that every pair gets equal work.
-//   instantiations  <BN, A_MN, B_MN, AUX>: AUX = epilogues that read a second matrix.  Separate because the
-//                 epilogue lives at the 168-register cap (10 warps → 3 per SM sub-partition).
+//   instantiations  <BN, A_MN, B_MN, AUX, EW, EPI>: AUX = epilogues that read a second matrix.  Separate because the
+//                 epilogue lives at the 168-register cap (10 warps → 3 per SM sub-partition); EW = 16 with a compile-time
+//                 epilogue EPI lives at 96 (18 warps → 5 on one sub-partition).
 // Diagnostics: VITK_GEMM_DBG ablation bits (Gemm2Params::dbg) and, in builds with -DVITK_GEMM_STAMPS=1, clock
 // stamps per K block / tile / CTA / launch (tools/gemm_timeline.py).
 #include <cuda.h>
